@@ -46,6 +46,22 @@ const char* modest_last_error(void);
 int64_t modest_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
+ * Stage B: bring scan frames into the fixed frame.
+ * Replaces transform_points() (utils/pointcloud_utils.py:11-19: [p,1] @ Tr^T in float32) and,
+ * optionally, remove_center() (pre_compute_pp_score.py:48-52, nuScenes history frames).
+ *   d_in (M,point_stride) f32; frame f owns rows [d_frame_off[f], d_frame_off[f+1])
+ *   d_T  (n_frames,16) f32 row-major 4x4 (the float32 matrix get_relative_pose returns)
+ *   h_center_box host float[4] {x_lo, x_hi, y_lo, y_hi}: rows with x_lo <= x < x_hi and
+ *        y_lo <= y < y_hi are removed when remove_center != 0 (written as NaN so that every
+ *        later distance test rejects them; row positions are preserved)
+ *   d_out (M,3) f32
+ * ------------------------------------------------------------------------------------------ */
+int modest_transform_frames_batch(const float* d_in, int point_stride,
+                                  const int64_t* d_frame_off, const float* d_T, int n_frames,
+                                  int64_t max_frame_points, int remove_center,
+                                  const float* h_center_box, float* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stage C+D: persistence-point (PP) score.
  * Replaces count_neighbors() + compute_ephe_score() (pre_compute_pp_score.py:54-75) and the
  * cKDTree builds at :188-190.
@@ -75,6 +91,185 @@ int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_q_off,
                           int64_t max_query_points, int64_t max_trav_points, double radius,
                           int grid_dim, int32_t* d_counts, const int64_t* d_count_off,
                           float* d_pp, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage E: RANSAC ground plane.
+ * Replaces estimate_plane() (utils/pointcloud_utils.py:44-65), i.e. sklearn's
+ * RANSACRegressor().fit(xy, z) with all defaults (trial loop: sklearn/linear_model/_ransac.py
+ * :447-560, an un-vendored dependency of the reference).
+ *
+ * Step 1, modest_plane_candidates_batch: keeps, in order, the points with z < max_hs and
+ *   x_lo < x < x_hi, y_lo < y < y_hi (pointcloud_utils.py:45-49) and computes the residual
+ *   threshold MAD(z) in float32 (_ransac.py:396-398).
+ *     d_ptc (NP,point_stride) f32 rows [x,y,z,...]; scan s owns rows [d_off[s], d_off[s+1])
+ *     d_cand (NP,3) f32 out: scan s's candidates are packed at row d_off[s]
+ *     d_n_cand (n_scans) i32 out;  d_thr (n_scans) f32 out
+ * Step 2, modest_ransac_fit_batch: scores `max_trials` minimal-set hypotheses per scan,
+ *   replays sklearn's sequential accept / dynamic-early-stop rules over them, refits on the
+ *   consensus set and emits the plane [a,b,c,d] (c > 0) of pointcloud_utils.py:53-62.
+ *     d_triples  (n_scans,max_trials,3) i32 indices into each scan's candidate list -- drawn by
+ *                the caller (parity: numpy's global RandomState, like sklearn) -- or NULL to
+ *                draw them on the device from `seed` (throughput mode)
+ *     d_plane    (n_scans,4) f64 out (NaN when no valid consensus set exists)
+ *     d_model    (n_scans,3) f64 out or NULL: the float32 coef_[0], coef_[1], intercept_
+ *     d_info     (n_scans,4) i32 out: n_candidates, n_trials_ consumed, best trial, n_inliers
+ *     d_triples_out  optional (n_scans,max_trials,3) i32: the triples actually used
+ *     d_inlier_mask  optional (NP) u8: consensus mask per candidate (packed like d_cand)
+ * ------------------------------------------------------------------------------------------ */
+int modest_plane_candidates_batch(const float* d_ptc, int point_stride, const int64_t* d_off,
+                                  int n_scans, float max_hs, float x_lo, float x_hi, float y_lo,
+                                  float y_hi, float* d_cand, int32_t* d_n_cand, float* d_thr,
+                                  void* stream);
+size_t modest_ransac_workspace_bytes(int n_scans, int max_trials);
+int modest_ransac_fit_batch(const float* d_cand, const int64_t* d_off, const int32_t* d_n_cand,
+                            const float* d_thr, int n_scans, int64_t max_points,
+                            const int32_t* d_triples, uint64_t seed, int max_trials,
+                            double* d_plane, double* d_model, int32_t* d_info,
+                            int32_t* d_triples_out, uint8_t* d_inlier_mask, void* d_ws,
+                            size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stages F+G: ground removal and range gate, compacted.
+ * Replaces above_plane()/distance_to_plane() (utils/pointcloud_utils.py:68-81) and the
+ * limit_range product of generate_mask.py:57-65.  A point survives iff
+ *     NOT( (p.n + d)/|n| < offset  AND  only_x_lo < x < only_x_hi AND only_y_lo < y < only_y_hi )
+ *     AND lim_x_lo < x <= lim_x_hi AND lim_y_lo < y <= lim_y_hi
+ *   d_planes      (n_scans,4) f64;  d_pp (NP) f32 PP scores
+ *   h_only_range  host float[4] {x_lo,x_hi,y_lo,y_hi} or NULL (the reference's only_range=None)
+ *   h_limit_range host float[4]
+ *   d_kept        (NP,4) f32 out: surviving points as (x,y,z,pp), original order, packed at
+ *                 row d_off[s];  d_kept_idx (NP) i32 out: their indices within the scan;
+ *   d_n_kept      (n_scans) i32 out;  d_mask (NP) u8 out or NULL: the boolean final_mask
+ * ------------------------------------------------------------------------------------------ */
+int modest_ground_mask_batch(const float* d_ptc, int point_stride, const int64_t* d_off,
+                             const float* d_pp, const double* d_planes, int n_scans,
+                             double offset, const float* h_only_range,
+                             const float* h_limit_range, float* d_kept, int32_t* d_kept_idx,
+                             int32_t* d_n_kept, uint8_t* d_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage H: mutual-kNN AND radius graph with L1 PP-score weights.
+ * Replaces precompute_affinity_matrix(ptc, pp, 'radius_mutual_knn', 'l1', n_neighbors, radius)
+ * (utils/clustering_utils.py:32-48; sklearn kneighbors_graph / radius_neighbors_graph).
+ * Edge (i,j), i != j:  j among the n_neighbors nearest other points of i, i among those of j,
+ * and dx*dx+dy*dy+dz*dz <= radius*radius, all in sequential f64 on the f32 coordinates;
+ * weight = |pp_i - pp_j| in f32.  Output is a fixed-width adjacency: row i of scan s lives at
+ * row d_off[s]+i and holds d_nbr_cnt entries (unordered) of d_nbr (neighbour index within the
+ * kept list) and d_nbr_w.  *d_flags (one i32) gets bit0/bit1 set if distance ties made a
+ * k-th neighbour ambiguous / overflowed a row (never on duplicate-free data).
+ * ------------------------------------------------------------------------------------------ */
+size_t modest_graph_workspace_bytes(int n_scans, int64_t n_points_total, int n_neighbors,
+                                    int grid_dim);
+int modest_affinity_graph_batch(const float* d_kept, const int64_t* d_off,
+                                const int32_t* d_n_kept, int n_scans, int64_t n_points_total,
+                                int64_t max_points, int n_neighbors, double radius,
+                                int grid_dim, int32_t* d_nbr, float* d_nbr_w,
+                                int32_t* d_nbr_cnt, int32_t* d_flags, void* d_ws,
+                                size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage I: DBSCAN on that graph.
+ * Replaces sklearn.cluster.DBSCAN(metric='precomputed', eps, min_samples).fit(graph).labels_
+ * (generate_mask.py:75-81): neighbourhood(i) = {j : edge, (double)w <= eps} + {i}; core iff
+ * its size >= min_samples; clusters = connected components of core-core edges, numbered by
+ * their smallest member index; a border point takes the smallest cluster id among its core
+ * neighbours; everything else -1.
+ *   d_labels_kept (NP) i32 out: label per kept point;  d_labels_full (NP) i32 out: label per
+ *   original point (-1 for removed points), i.e. the `labels` array of generate_mask.py:76-81
+ *   d_n_clusters  (n_scans) i32 out
+ * ------------------------------------------------------------------------------------------ */
+size_t modest_dbscan_workspace_bytes(int64_t n_points_total);
+int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept,
+                        const int32_t* d_kept_idx, int n_scans, int64_t n_points_total,
+                        int64_t max_points, int n_neighbors, const int32_t* d_nbr,
+                        const float* d_nbr_w, const int32_t* d_nbr_cnt, double eps,
+                        int min_samples, int32_t* d_labels_kept, int32_t* d_labels_full,
+                        int32_t* d_n_clusters, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stages J-M: cluster filtering, box fitting, volume gate, final labels.
+ * Replaces filter_labels()/is_valid_cluster() (utils/clustering_utils.py:94-135, given the
+ * second plane), Calibration.project_velo_to_rect (utils/kitti_util.py:293-329),
+ * get_obj(..., 'closeness_to_edge') (utils/pointcloud_utils.py:167-216,278-317) and the volume
+ * gate + label compaction of generate_mask.py:92-103.
+ *   d_labels          (NP) i32 DBSCAN labels per original point (-1 = none), d_n_clusters (S)
+ *   d_planes          (S,4) f64: the SECOND plane (filter_labels' own RANSAC fit)
+ *   d_calib           (S,21) f64: Tr_velo_to_cam (3x4 row-major) then R0_rect (3x3)
+ *   d_rect_in         optional (NP,3) f64: rect-camera coordinates of every point; when given
+ *                     they are used instead of projecting d_ptc with d_calib (the operator-level
+ *                     get_obj() receives rect coordinates directly)
+ *   h_gates           host double[8]: min_points, max_min_height, min_max_height,
+ *                     percentile/100 evaluated in float32, min_percentile_pp_score,
+ *                     min_volume, max_volume, d0 (closeness floor, 1e-2)
+ *   d_trig            (4,n_angles) f64: cos(a), sin(a), cos(a+pi/2), sin(a+pi/2) for the search
+ *                     headings a -- a constant table the caller evaluates with the host libm so
+ *                     that it holds the same values numpy gives the reference
+ *   d_angles          (2,n_angles) f64: a and a+pi/2
+ *   d_labels_filtered (NP) i32 out: filter_labels() result (0 = background, 1..K)
+ *   d_labels_final    (NP) i32 out: labels after the volume gate, compacted (the seg .npy)
+ *   d_boxes           (S,max_boxes,8) f64 out: t.x t.y t.z l w h ry volume per surviving box
+ *   d_n_boxes, d_n_valid (S) i32 out;  d_flags (1) i32 out: bit2 cluster capacity, bit3 empty
+ *                     footprint, bit4 box capacity exceeded
+ * ------------------------------------------------------------------------------------------ */
+size_t modest_filter_workspace_bytes(int n_scans, int64_t n_points_total, int max_clusters);
+int modest_filter_and_fit_batch(const float* d_ptc, int point_stride, const int64_t* d_off,
+                                const float* d_pp, const int32_t* d_labels,
+                                const int32_t* d_n_clusters, const double* d_planes,
+                                const double* d_calib, const double* d_rect_in, int n_scans,
+                                int64_t n_points_total,
+                                int64_t max_points, int max_clusters, int max_boxes,
+                                const double* h_gates, const double* d_trig,
+                                const double* d_angles, int n_angles,
+                                int32_t* d_labels_filtered, int32_t* d_labels_final,
+                                double* d_boxes, int32_t* d_n_boxes, int32_t* d_n_valid,
+                                int32_t* d_flags, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage N: rotated BEV IoU / overlap / NMS on boxes [x, y, z, dx, dy, dz, heading] (f32).
+ * Drop-in for the reference's pybind11 module iou3d_nms_cuda
+ * (utils/iou3d_nms/src/iou3d_nms_api.cpp:11-17; host wrappers iou3d_nms.cpp:48-188;
+ * kernels iou3d_nms_kernel.cu:236-372):
+ *   boxes_iou_bev_gpu     -> modest_boxes_iou_bev      out (num_a,num_b) f32
+ *   boxes_overlap_bev_gpu -> modest_boxes_overlap_bev
+ *   nms_gpu               -> modest_nms_bev    boxes sorted by score; writes the kept indices
+ *   nms_normal_gpu        -> modest_nms_normal (axis-aligned IoU)
+ * The NMS calls return the number kept through *h_num_out and therefore synchronise `stream`
+ * (as the reference does with its blocking cudaMemcpy); d_keep (device, i64) and h_keep
+ * (host, i64) are both optional.
+ * modest_seed_nms_batch is the batched form of objs_nms() (utils/pointcloud_utils.py:320-344,
+ * use_score_rank=False): per scan, K x K IoU of [t.x,t.z,0,l,w,h,-ry] (rounded to f32), visit
+ * boxes by descending self-IoU (ties: larger index first), suppress IoU > thresh.
+ *   d_boxes (S,max_boxes,8) f64 rows as written by modest_filter_and_fit_batch
+ *   d_iou_or_null (S,max_boxes,max_boxes) f32 out (optional), d_iou_ws same shape scratch
+ *   d_keep (S,max_boxes) u8 out
+ * ------------------------------------------------------------------------------------------ */
+int modest_boxes_iou_bev(const float* d_boxes_a, int num_a, const float* d_boxes_b, int num_b,
+                         float* d_iou, void* stream);
+int modest_boxes_overlap_bev(const float* d_boxes_a, int num_a, const float* d_boxes_b,
+                             int num_b, float* d_overlap, void* stream);
+size_t modest_nms_workspace_bytes(int n);
+int modest_nms_bev(const float* d_boxes, int n, float thresh, int64_t* d_keep, int64_t* h_keep,
+                   int* h_num_out, void* d_ws, size_t ws_bytes, void* stream);
+int modest_nms_normal(const float* d_boxes, int n, float thresh, int64_t* d_keep,
+                      int64_t* h_keep, int* h_num_out, void* d_ws, size_t ws_bytes,
+                      void* stream);
+int modest_seed_nms_batch(const double* d_boxes, const int32_t* d_n_boxes, int n_scans,
+                          int max_boxes, float thresh, float* d_iou_or_null, float* d_iou_ws,
+                          uint8_t* d_keep, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage O (host): field-of-view gate + KITTI label text.
+ * Replaces is_within_fov() and objs2label() (utils/pointcloud_utils.py:347-379, with
+ * compute_box_3d / project_to_image, utils/kitti_util.py:383-389,405-478).  All pointers are
+ * HOST pointers.  h_boxes (n,8) f64 rows t.x t.y t.z l w h ry volume; h_keep_in optional
+ * (n) u8; h_P the 3x4 P2 matrix; h_scores optional (n) -> the `with_score` line format.
+ * Writes '\n'-joined "%.4f" lines without trailing newline (NUL-terminated) into h_text.
+ * ------------------------------------------------------------------------------------------ */
+int modest_kitti_labels_host(const double* h_boxes, int n, const uint8_t* h_keep_in,
+                             const double* h_P, int fov_only, int image_h, int image_w,
+                             const char* obj_type, const double* h_scores, char* h_text,
+                             size_t text_cap, size_t* h_len, int* h_n_out,
+                             uint8_t* h_kept_out);
 
 #ifdef __cplusplus
 }

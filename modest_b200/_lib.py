@@ -27,9 +27,35 @@ SIGNATURES = {
     "modest_abi_version": (C.c_int, []),
     "modest_last_error": (C.c_char_p, []),
     "modest_launch_count": (_i64, []),
+    "modest_transform_frames_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp]),
     "modest_pp_workspace_bytes": (_sz, [C.c_int, _i64, _i64, C.c_int]),
     "modest_pp_score_batch": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _i64, _i64, _i64,
                                         _i64, _f64, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "modest_plane_candidates_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _f32, _f32, _f32, _f32, _f32,
+                                                _vp, _vp, _vp, _vp]),
+    "modest_ransac_workspace_bytes": (_sz, [C.c_int, C.c_int]),
+    "modest_ransac_fit_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _i64, _vp, C.c_uint64, C.c_int,
+                                          _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "modest_ground_mask_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _f64, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _vp]),
+    "modest_graph_workspace_bytes": (_sz, [C.c_int, _i64, C.c_int, C.c_int]),
+    "modest_affinity_graph_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, C.c_int, _f64, C.c_int,
+                                              _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "modest_dbscan_workspace_bytes": (_sz, [_i64]),
+    "modest_dbscan_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, C.c_int, _vp, _vp, _vp, _f64,
+                                      C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "modest_filter_workspace_bytes": (_sz, [C.c_int, _i64, C.c_int]),
+    "modest_filter_and_fit_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _i64,
+                                              C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp,
+                                              _vp, _vp, _vp, _sz, _vp]),
+    "modest_boxes_iou_bev": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "modest_boxes_overlap_bev": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp]),
+    "modest_nms_workspace_bytes": (_sz, [C.c_int]),
+    "modest_nms_bev": (C.c_int, [_vp, C.c_int, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "modest_nms_normal": (C.c_int, [_vp, C.c_int, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "modest_seed_nms_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f32, _vp, _vp, _vp, _vp]),
+    "modest_kitti_labels_host": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                           _vp, _vp, _sz, _vp, _vp, _vp]),
 }
 
 

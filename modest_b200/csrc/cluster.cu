@@ -1,0 +1,580 @@
+// Stages F-I: ground/range masks, mutual-kNN ^ radius graph with |delta pp| weights, DBSCAN.
+//
+// Reference behaviour:
+//   F  above_plane / distance_to_plane        utils/pointcloud_utils.py:68-81
+//   G  limit_range mask                       generate_mask.py:61-65
+//   H  precompute_affinity_matrix(..., 'radius_mutual_knn', 'l1', k, radius)
+//                                             utils/clustering_utils.py:32-48 (sklearn
+//      kneighbors_graph / radius_neighbors_graph: f64 squared distances on f32 coordinates,
+//      self excluded, j in kNN_k(i) and i in kNN_k(j) and d2 <= radius^2)
+//   I  sklearn DBSCAN(metric='precomputed')   generate_mask.py:77-81; semantics of
+//      sklearn/cluster/_dbscan.py:427-463 + _dbscan_inner.pyx (un-vendored dependency).
+//
+// Data layout (per scan s, rows at off[s] in every per-point array):
+//   kept[i]   float4 (x, y, z, pp) of the i-th surviving point, original order preserved
+//   kept_idx  index of that point in the scan;  n_kept[s] on the device
+//   rk2[i]    f64: squared distance to the k-th nearest other point (+inf when fewer than k
+//             other points lie within the radius -- then every one of them is a k-neighbour)
+//   knn       (row, k) i32 candidate lists: { j != i : d2(i,j) <= min(rk2[i], radius^2) }
+//   nbr / nbr_w / nbr_cnt: the mutual edges of row i and their f32 weights |pp_i - pp_j|
+#include "grid2d.cuh"
+
+namespace modest {
+extern void note_launch(int n);
+
+// ---- F+G: masks and order-preserving compaction ----------------------------------------------
+struct MaskCfg {
+  double offset;
+  float only_x_lo, only_x_hi, only_y_lo, only_y_hi;   // plane_estimate.range (strict both sides)
+  int use_only_range;
+  float lim_x_lo, lim_x_hi, lim_y_lo, lim_y_hi;       // limit_range ( lo < v <= hi )
+};
+
+__device__ __forceinline__ double plane_distance(float x, float y, float z, const double* pl, double nrm) {
+  // ptc(f32) @ plane[:3](f64) + plane[3], then / ||n||   (pointcloud_utils.py:76-81)
+  // numpy hands the (N,3) @ (3,) product to OpenBLAS dgemv, whose kernel rounds as
+  // fma(z,c, fma(x,a, y*b)) (checked against numpy in tests/test_host_numerics.py)
+  double d = __fma_rn((double)z, pl[2], __fma_rn((double)x, pl[0], __dmul_rn((double)y, pl[1])));
+  d = __dadd_rn(d, pl[3]);
+  return __ddiv_rn(d, nrm);
+}
+__device__ __forceinline__ double plane_norm(const double* pl) {
+  return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(pl[0], pl[0]), __dmul_rn(pl[1], pl[1])), __dmul_rn(pl[2], pl[2])));
+}
+
+__global__ void __launch_bounds__(1024) ground_mask_compact_kernel(
+    const float* __restrict__ ptc, int stride, const int64_t* __restrict__ off, const float* __restrict__ pp,
+    const double* __restrict__ planes, MaskCfg cfg, float4* __restrict__ kept, int32_t* __restrict__ kept_idx,
+    int32_t* __restrict__ n_kept, uint8_t* __restrict__ mask_out) {
+  const int s = blockIdx.x;
+  const int64_t beg = off[s];
+  const int n = (int)(off[s + 1] - beg);
+  double pl[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) pl[k] = planes[4 * s + k];
+  const double nrm = plane_norm(pl);
+  __shared__ int warp_cnt[32];
+  __shared__ int tile_total;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int base = 0;
+  for (int t0 = 0; t0 < n; t0 += 1024) {
+    const int i = t0 + threadIdx.x;
+    float x = 0, y = 0, z = 0, v = 0;
+    bool keep = false;
+    if (i < n) {
+      const float* p = ptc + (size_t)stride * (beg + i);
+      x = p[0]; y = p[1]; z = p[2];
+      v = pp[beg + i];
+      bool drop = plane_distance(x, y, z, pl, nrm) < cfg.offset;
+      if (cfg.use_only_range)
+        drop = drop && (x < cfg.only_x_hi) && (x > cfg.only_x_lo) && (y < cfg.only_y_hi) && (y > cfg.only_y_lo);
+      const bool in_lim = (x <= cfg.lim_x_hi) && (x > cfg.lim_x_lo) && (y <= cfg.lim_y_hi) && (y > cfg.lim_y_lo);
+      keep = !drop && in_lim;
+      if (mask_out) mask_out[beg + i] = keep ? 1 : 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[w] = __popc(bal);
+    __syncthreads();
+    if (w == 0) {
+      int c = warp_cnt[lane], inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      warp_cnt[lane] = inc - c;
+      if (lane == 31) tile_total = inc;
+    }
+    __syncthreads();
+    if (keep) {
+      const int pos = base + warp_cnt[w] + __popc(bal & ((1u << lane) - 1u));
+      kept[beg + pos] = make_float4(x, y, z, v);
+      kept_idx[beg + pos] = i;
+    }
+    base += tile_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_kept[s] = base;
+}
+
+// ---- H.1: k-th neighbour distance and candidate lists, one warp per point ---------------------
+constexpr int kBins = 256;
+constexpr int kMaxDepth = 6;
+
+struct BinChain {            // nested linear binning of d2: level l keeps bin sel[l] of [lo[l], lo[l]+256/scale[l])
+  double lo[kMaxDepth], scale[kMaxDepth];
+  int sel[kMaxDepth];
+  int depth;
+};
+
+__device__ __forceinline__ int bin_of(double d2, double lo, double scale) {
+  const double t = (d2 - lo) * scale;
+  int b = (int)t;
+  return b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
+}
+
+// true iff d2 passes every closed level of the chain; *last = bin at the open level `depth`
+__device__ __forceinline__ bool chain_bin(const BinChain& c, double d2, int* last) {
+  for (int l = 0; l < c.depth; ++l)
+    if (bin_of(d2, c.lo[l], c.scale[l]) != c.sel[l]) return false;
+  *last = bin_of(d2, c.lo[c.depth], c.scale[c.depth]);
+  return true;
+}
+
+template <typename F>
+__device__ __forceinline__ void for_each_candidate(const float4* __restrict__ sorted, const int* __restrict__ cells,
+                                                   int G, int cx, int cy, int L, int self_pos, F f) {
+  const int lane = threadIdx.x & 31;
+  const int xa = clampi(cx - L, 0, G - 1), xb = clampi(cx + L, 0, G - 1);
+  const int ya = clampi(cy - L, 0, G - 1), yb = clampi(cy + L, 0, G - 1);
+  for (int y = ya; y <= yb; ++y) {
+    const int kb = __ldg(cells + y * G + xa), ke = __ldg(cells + y * G + xb + 1);
+    for (int k0 = kb; k0 < ke; k0 += 32) {
+      const int k = k0 + lane;
+      const bool live = k < ke && k != self_pos;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) q = __ldg(sorted + k);
+      f(live, q);            // called convergently by the whole warp
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) knn_select_kernel(
+    const float4* __restrict__ sorted_all, const int* __restrict__ cells_all, const GridMeta* __restrict__ meta,
+    const int64_t* __restrict__ off, int G, int k_nn, double r2_max, int L_fine, double r2_fine, int L_coarse,
+    double* __restrict__ rk2_all, int32_t* __restrict__ knn_all, int32_t* __restrict__ knn_cnt_all,
+    int32_t* __restrict__ flags) {
+  const int s = blockIdx.y;
+  const GridMeta m = meta[s];
+  const int n = m.n;
+  const float4* __restrict__ sorted = sorted_all + off[s];
+  const int* __restrict__ cells = cells_all + (size_t)s * cell_stride(G);
+  __shared__ int hist_sh[4][kBins];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int* hist = hist_sh[wib];
+  const int warps_per_grid = gridDim.x * 4;
+
+  for (int pos = blockIdx.x * 4 + wib; pos < n; pos += warps_per_grid) {
+    const float4 p = sorted[pos];
+    const int i = __float_as_int(p.w);
+    const int cx = cell_coord(p.x, m.x0, m.inv_cell), cy = cell_coord(p.y, m.y0, m.inv_cell);
+    double rk2 = __longlong_as_double(0x7ff0000000000000ll);   // +inf
+    int L = L_fine;
+    double R2 = r2_fine;
+    bool bounded = false;          // true once we know >= k others lie within R2 at level L
+    for (int level = 0; level < 2 && !bounded; ++level) {
+      if (level == 1) { L = L_coarse; R2 = r2_max; }
+      // ---- round 0: histogram of d2 over [0, R2] ----
+      BinChain ch;
+      ch.depth = 0;
+      ch.lo[0] = 0.0;
+      ch.scale[0] = (double)kBins / (R2 * (1.0 + 1e-12) + 1e-300);
+      int need = k_nn;             // rank (1-based) of the wanted element among those in the open range
+      bool done = false;
+      for (int round = 0; round < kMaxDepth && !done; ++round) {
+        for (int b = lane; b < kBins; b += 32) hist[b] = 0;
+        __syncwarp();
+        for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
+          if (live) {
+            const double d2 = sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z);
+            int b;
+            if (d2 <= R2 && chain_bin(ch, d2, &b)) atomicAdd(&hist[b], 1);
+          }
+        });
+        __syncwarp();
+        // warp prefix over 256 bins: lane owns 8 consecutive bins
+        int loc[8], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { loc[j] = hist[lane * 8 + j]; tot += loc[j]; }
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int u = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += u;
+        }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        if (round == 0 && total < k_nn) break;   // fewer than k others within R2 at this level
+        bounded = true;
+        // find the bin holding rank `need`
+        int exc = inc - tot, selbin = -1, below = 0, inbin = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (selbin < 0 && exc + loc[j] >= need && need > exc) { selbin = lane * 8 + j; below = exc; inbin = loc[j]; }
+          exc += loc[j];
+        }
+        const unsigned who = __ballot_sync(0xffffffffu, selbin >= 0);
+        const int src = __ffs(who) - 1;
+        selbin = __shfl_sync(0xffffffffu, selbin, src);
+        below = __shfl_sync(0xffffffffu, below, src);
+        inbin = __shfl_sync(0xffffffffu, inbin, src);
+        need -= below;
+        ch.sel[ch.depth] = selbin;
+        if (inbin <= 32 || round == kMaxDepth - 1) {
+          // ---- gather the <= 32 members of the selected bin, rank them exactly ----
+          const int closed = ch.depth + 1;
+          double mine = __longlong_as_double(0x7ff0000000000000ll);
+          int have = 0;
+          for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
+            bool in = false;
+            double d2 = 0.0;
+            if (live) {
+              d2 = sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z);
+              if (d2 <= R2) {
+                in = true;
+                for (int l = 0; l < closed; ++l) in = in && (bin_of(d2, ch.lo[l], ch.scale[l]) == ch.sel[l]);
+              }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            const int slot = have + __popc(bal & ((1u << lane) - 1u));
+            // hand each member to the lane whose id equals its slot
+            for (unsigned rem = bal; rem; rem &= rem - 1) {
+              const int srcl = __ffs(rem) - 1;
+              const int dst = __shfl_sync(0xffffffffu, slot, srcl);
+              const double v = __shfl_sync(0xffffffffu, d2, srcl);
+              if (lane == dst) mine = v;
+            }
+            have += __popc(bal);
+          });
+          if (inbin > 32) { if (lane == 0) atomicOr(flags, 1); }   // unresolved tie block
+          // exact rank: number of members strictly smaller (ties broken by lane)
+          int rank = 0;
+          for (int l2 = 0; l2 < 32; ++l2) {
+            const double v = __shfl_sync(0xffffffffu, mine, l2);
+            rank += (v < mine) || (v == mine && l2 < lane);
+          }
+          const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < have);
+          const int srcl = hitl ? __ffs(hitl) - 1 : 0;
+          rk2 = __shfl_sync(0xffffffffu, mine, srcl);
+          done = true;
+        } else {
+          // descend: split the selected bin into 256 sub-bins
+          const double w = 1.0 / ch.scale[ch.depth];
+          ch.lo[ch.depth + 1] = ch.lo[ch.depth] + (double)selbin * w;
+          ch.scale[ch.depth + 1] = ch.scale[ch.depth] * (double)kBins;
+          ch.depth += 1;
+        }
+      }
+    }
+    // ---- emit { j : d2 <= min(rk2, r2_max) } using the level that decided rk2 -------------
+    const double cut = fmin(rk2, r2_max);
+    int32_t* out = knn_all + ((size_t)off[s] + i) * k_nn;
+    int have = 0;
+    for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
+      bool in = false;
+      if (live) in = sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z) <= cut;
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      const int slot = have + __popc(bal & ((1u << lane) - 1u));
+      if (in && slot < k_nn) out[slot] = __float_as_int(q.w);
+      have += __popc(bal);
+    });
+    if (lane == 0) {
+      if (have > k_nn) { atomicOr(flags, 2); have = k_nn; }   // ties beyond k: list truncated
+      rk2_all[off[s] + i] = rk2;
+      knn_cnt_all[off[s] + i] = have;
+    }
+  }
+}
+
+// ---- H.2: mutual test + L1 pp weights -------------------------------------------------------------
+__global__ void __launch_bounds__(256) mutual_edges_kernel(
+    const float4* __restrict__ kept, const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept,
+    int k_nn, const double* __restrict__ rk2, const int32_t* __restrict__ knn, const int32_t* __restrict__ knn_cnt,
+    int32_t* __restrict__ nbr, float* __restrict__ nbr_w, int32_t* __restrict__ nbr_cnt) {
+  const int s = blockIdx.y;
+  const int n = n_kept[s];
+  const int64_t base = off[s];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < n; i += nwarps) {
+    const float4 p = kept[base + i];
+    const int m = knn_cnt[base + i];
+    const int32_t* row = knn + (size_t)(base + i) * k_nn;
+    int have = 0;
+    for (int c0 = 0; c0 < m; c0 += 32) {
+      const int c = c0 + lane;
+      bool in = false;
+      int j = 0;
+      float w = 0.f;
+      if (c < m) {
+        j = row[c];
+        const float4 q = kept[base + j];
+        const double d2 = sqdist_f64_seq(q.x, q.y, q.z, p.x, p.y, p.z);   // same expression as row j used
+        in = d2 <= rk2[base + j];
+        w = fabsf(__fsub_rn(p.w, q.w));
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      if (in) {
+        const int slot = have + __popc(bal & ((1u << lane) - 1u));
+        nbr[(size_t)(base + i) * k_nn + slot] = j;
+        nbr_w[(size_t)(base + i) * k_nn + slot] = w;
+      }
+      have += __popc(bal);
+    }
+    if (lane == 0) nbr_cnt[base + i] = have;
+  }
+}
+
+// ---- I: DBSCAN ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dbscan_core_kernel(
+    const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, int k_nn, const float* __restrict__ nbr_w,
+    const int32_t* __restrict__ nbr_cnt, double eps, int min_samples, uint8_t* __restrict__ core,
+    int32_t* __restrict__ parent) {
+  const int s = blockIdx.y;
+  const int n = n_kept[s];
+  const int64_t base = off[s];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int m = nbr_cnt[base + i];
+    const float* w = nbr_w + (size_t)(base + i) * k_nn;
+    int deg = 1;                                   // the point itself (sklearn adds the diagonal)
+    for (int c = 0; c < m; ++c) deg += ((double)w[c] <= eps);
+    core[base + i] = deg >= min_samples;
+    parent[base + i] = i;
+  }
+}
+
+__device__ __forceinline__ int uf_find(int32_t* parent, int a) {
+  int p = parent[a];
+  while (p != a) {
+    const int gp = parent[p];
+    if (gp != p) parent[a] = gp;    // path halving (benign race: parents only ever decrease)
+    a = p;
+    p = parent[a];
+  }
+  return a;
+}
+__device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
+  while (true) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }       // a > b: hang the larger root under the smaller
+    const int old = atomicCAS(&parent[a], a, b);
+    if (old == a) return;
+  }
+}
+
+__global__ void __launch_bounds__(256) dbscan_union_kernel(
+    const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, int k_nn, const int32_t* __restrict__ nbr,
+    const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt, double eps, const uint8_t* __restrict__ core,
+    int32_t* __restrict__ parent) {
+  const int s = blockIdx.y;
+  const int n = n_kept[s];
+  const int64_t base = off[s];
+  const int64_t total = (int64_t)n * k_nn;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / k_nn), c = (int)(e % k_nn);
+    if (c >= nbr_cnt[base + i] || !core[base + i]) continue;
+    const int j = nbr[(size_t)(base + i) * k_nn + c];
+    if (j >= i || !core[base + j]) continue;       // each undirected edge once
+    if ((double)nbr_w[(size_t)(base + i) * k_nn + c] <= eps) uf_union(parent + base, i, j);
+  }
+}
+
+// One CTA per scan: number the clusters by their smallest core index (sklearn visits points in
+// index order), label cores, then borders (smallest cluster id among core neighbours), and
+// scatter into the full-size label array.
+__global__ void __launch_bounds__(1024) dbscan_label_kernel(
+    const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, const int32_t* __restrict__ kept_idx,
+    int k_nn, const int32_t* __restrict__ nbr, const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt,
+    double eps, const uint8_t* __restrict__ core, int32_t* __restrict__ parent, int32_t* __restrict__ root_rank,
+    int32_t* __restrict__ labels_kept, int32_t* __restrict__ labels_full, int32_t* __restrict__ n_clusters) {
+  const int s = blockIdx.x;
+  const int n = n_kept[s];
+  const int64_t base = off[s];
+  const int n_full = (int)(off[s + 1] - base);
+  int32_t* par = parent + base;
+  __shared__ int warp_cnt[32];
+  __shared__ int tile_total;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < n_full; i += blockDim.x) labels_full[base + i] = -1;
+  // roots are exactly the core points that are their own parent; rank them in index order
+  int running = 0;
+  for (int t0 = 0; t0 < n; t0 += 1024) {
+    const int i = t0 + threadIdx.x;
+    const bool is_root = i < n && core[base + i] && par[i] == i;
+    const unsigned bal = __ballot_sync(0xffffffffu, is_root);
+    if (lane == 0) warp_cnt[w] = __popc(bal);
+    __syncthreads();
+    if (w == 0) {
+      int c = warp_cnt[lane], inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      warp_cnt[lane] = inc - c;
+      if (lane == 31) tile_total = inc;
+    }
+    __syncthreads();
+    if (is_root) root_rank[base + i] = running + warp_cnt[w] + __popc(bal & ((1u << lane) - 1u));
+    running += tile_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_clusters[s] = running;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (core[base + i]) {
+      int r = i;
+      while (par[r] != r) r = par[r];
+      labels_kept[base + i] = root_rank[base + r];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int lab;
+    if (core[base + i]) {
+      lab = labels_kept[base + i];
+    } else {
+      lab = 0x7fffffff;
+      const int m = nbr_cnt[base + i];
+      for (int c = 0; c < m; ++c) {
+        const int j = nbr[(size_t)(base + i) * k_nn + c];
+        if (core[base + j] && (double)nbr_w[(size_t)(base + i) * k_nn + c] <= eps) lab = min(lab, labels_kept[base + j]);
+      }
+      if (lab == 0x7fffffff) lab = -1;
+    }
+    labels_full[base + kept_idx[base + i]] = lab;
+    if (!core[base + i]) root_rank[base + i] = lab;   // stash; copied back below
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (!core[base + i]) labels_kept[base + i] = root_rank[base + i];
+}
+
+}  // namespace modest
+
+using namespace modest;
+
+extern "C" int modest_ground_mask_batch(const float* d_ptc, int point_stride, const int64_t* d_off,
+                                        const float* d_pp, const double* d_planes, int n_scans, double offset,
+                                        const float* h_only_range, const float* h_limit_range, float* d_kept,
+                                        int32_t* d_kept_idx, int32_t* d_n_kept, uint8_t* d_mask, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_scans <= 0) return MODEST_OK;
+  MODEST_REQUIRE(d_ptc && d_off && d_pp && d_planes && h_limit_range && d_kept && d_kept_idx && d_n_kept,
+                 "ground_mask: null pointer argument");
+  MODEST_REQUIRE(point_stride >= 3, "ground_mask: point_stride %d < 3", point_stride);
+  MaskCfg c;
+  c.offset = offset;
+  c.use_only_range = h_only_range != nullptr;
+  if (h_only_range) { c.only_x_lo = h_only_range[0]; c.only_x_hi = h_only_range[1]; c.only_y_lo = h_only_range[2]; c.only_y_hi = h_only_range[3]; }
+  else { c.only_x_lo = c.only_x_hi = c.only_y_lo = c.only_y_hi = 0.f; }
+  c.lim_x_lo = h_limit_range[0]; c.lim_x_hi = h_limit_range[1]; c.lim_y_lo = h_limit_range[2]; c.lim_y_hi = h_limit_range[3];
+  ground_mask_compact_kernel<<<n_scans, 1024, 0, stream>>>(d_ptc, point_stride, d_off, d_pp, d_planes, c,
+                                                           reinterpret_cast<float4*>(d_kept), d_kept_idx, d_n_kept, d_mask);
+  MODEST_LAUNCH_CHECK("ground_mask_compact_kernel");
+  note_launch(1);
+  return MODEST_OK;
+}
+
+static const float kGraphCell = 0.5f;        // fine cell edge of the kNN grid [m]
+static const float kGraphSlack = 1.001f;
+
+static int graph_levels(double radius, int* L_coarse) {
+  int L = (int)ceil(radius / (double)kGraphCell - 1e-9);
+  if (L < 1) L = 1;
+  *L_coarse = L;
+  return 1;   // fine level probes +-1 cell
+}
+
+extern "C" size_t modest_graph_workspace_bytes(int n_scans, int64_t n_points_total, int n_neighbors, int grid_dim) {
+  if (grid_dim <= 0) grid_dim = 288;
+  size_t b = 0;
+  auto add = [&](size_t bytes) { b = align_up(b, 256) + bytes; };
+  add(sizeof(GridMeta) * (size_t)n_scans);
+  add(sizeof(int) * (size_t)n_scans * cell_stride(grid_dim));
+  add(sizeof(float4) * (size_t)n_points_total);
+  add(sizeof(double) * (size_t)n_points_total);                    // rk2
+  add(sizeof(int32_t) * (size_t)n_points_total * n_neighbors);     // knn
+  add(sizeof(int32_t) * (size_t)n_points_total);                   // knn_cnt
+  return b + 256;
+}
+
+extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d_off, const int32_t* d_n_kept,
+                                           int n_scans, int64_t n_points_total, int64_t max_points,
+                                           int n_neighbors, double radius, int grid_dim, int32_t* d_nbr,
+                                           float* d_nbr_w, int32_t* d_nbr_cnt, int32_t* d_flags, void* d_ws,
+                                           size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_scans <= 0 || n_points_total <= 0) return MODEST_OK;
+  if (grid_dim <= 0) grid_dim = 288;
+  MODEST_REQUIRE(d_kept && d_off && d_n_kept && d_nbr && d_nbr_w && d_nbr_cnt && d_flags && d_ws,
+                 "affinity_graph: null pointer argument");
+  MODEST_REQUIRE(n_neighbors >= 1 && n_neighbors <= 1024, "affinity_graph: n_neighbors %d out of range", n_neighbors);
+  MODEST_REQUIRE(radius > 0.0 && radius <= 64.0, "affinity_graph: radius %g out of range", radius);
+  MODEST_REQUIRE(ws_bytes >= modest_graph_workspace_bytes(n_scans, n_points_total, n_neighbors, grid_dim),
+                 "affinity_graph: workspace too small");
+  MODEST_REQUIRE(n_scans <= 65535, "affinity_graph: more than 65535 scans in one launch");
+  const int G = grid_dim;
+  Arena ar(d_ws, ws_bytes);
+  GridMeta* meta = ar.take<GridMeta>(n_scans);
+  int* cells = ar.take<int>((size_t)n_scans * cell_stride(G));
+  float4* sorted = ar.take<float4>(n_points_total);
+  double* rk2 = ar.take<double>(n_points_total);
+  int32_t* knn = ar.take<int32_t>((size_t)n_points_total * n_neighbors);
+  int32_t* knn_cnt = ar.take<int32_t>(n_points_total);
+
+  const float cell = kGraphCell * kGraphSlack;
+  int rc = grid2d_build(d_kept, 4, d_off, d_n_kept, n_scans, max_points, cell, G, meta, cells, sorted, stream);
+  if (rc != MODEST_OK) return rc;
+  int L_coarse;
+  const int L_fine = graph_levels(radius, &L_coarse);
+  const double r2_max = radius * radius;
+  double r_fine = (double)kGraphCell * L_fine;            // a ball of this radius fits the +-L_fine cell window
+  if (r_fine > radius) r_fine = radius;
+  const double r2_fine = r_fine * r_fine;
+  int wblocks = (int)((max_points + 3) / 4);
+  if (wblocks < 1) wblocks = 1;
+  if (wblocks > 148 * 16) wblocks = 148 * 16;
+  MODEST_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t), stream));
+  knn_select_kernel<<<dim3(wblocks, n_scans), 128, 0, stream>>>(sorted, cells, meta, d_off, G, n_neighbors, r2_max,
+                                                               L_fine, r2_fine, L_coarse, rk2, knn, knn_cnt, d_flags);
+  MODEST_LAUNCH_CHECK("knn_select_kernel");
+  int mblocks = (int)((max_points * 32 + 255) / 256);
+  if (mblocks < 1) mblocks = 1;
+  if (mblocks > 148 * 8) mblocks = 148 * 8;
+  mutual_edges_kernel<<<dim3(mblocks, n_scans), 256, 0, stream>>>(reinterpret_cast<const float4*>(d_kept), d_off,
+                                                                 d_n_kept, n_neighbors, rk2, knn, knn_cnt, d_nbr,
+                                                                 d_nbr_w, d_nbr_cnt);
+  MODEST_LAUNCH_CHECK("mutual_edges_kernel");
+  note_launch(2);
+  return MODEST_OK;
+}
+
+extern "C" size_t modest_dbscan_workspace_bytes(int64_t n_points_total) {
+  return align_up((size_t)n_points_total, 256) + 2 * align_up(sizeof(int32_t) * (size_t)n_points_total, 256) + 512;
+}
+
+extern "C" int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept, const int32_t* d_kept_idx,
+                                   int n_scans, int64_t n_points_total, int64_t max_points, int n_neighbors,
+                                   const int32_t* d_nbr, const float* d_nbr_w, const int32_t* d_nbr_cnt, double eps,
+                                   int min_samples, int32_t* d_labels_kept, int32_t* d_labels_full,
+                                   int32_t* d_n_clusters, void* d_ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_scans <= 0 || n_points_total <= 0) return MODEST_OK;
+  MODEST_REQUIRE(d_off && d_n_kept && d_kept_idx && d_nbr && d_nbr_w && d_nbr_cnt && d_labels_kept &&
+                     d_labels_full && d_n_clusters && d_ws, "dbscan: null pointer argument");
+  MODEST_REQUIRE(ws_bytes >= modest_dbscan_workspace_bytes(n_points_total), "dbscan: workspace too small");
+  MODEST_REQUIRE(n_scans <= 65535, "dbscan: more than 65535 scans in one launch");
+  Arena ar(d_ws, ws_bytes);
+  uint8_t* core = ar.take<uint8_t>(n_points_total);
+  int32_t* parent = ar.take<int32_t>(n_points_total);
+  int32_t* root_rank = ar.take<int32_t>(n_points_total);
+  int pblocks = (int)((max_points + 255) / 256);
+  if (pblocks < 1) pblocks = 1;
+  dbscan_core_kernel<<<dim3(pblocks, n_scans), 256, 0, stream>>>(d_off, d_n_kept, n_neighbors, d_nbr_w, d_nbr_cnt,
+                                                                eps, min_samples, core, parent);
+  MODEST_LAUNCH_CHECK("dbscan_core_kernel");
+  int64_t eb = (max_points * n_neighbors + 255) / 256;
+  if (eb < 1) eb = 1;
+  if (eb > 148 * 32) eb = 148 * 32;
+  dbscan_union_kernel<<<dim3((unsigned)eb, n_scans), 256, 0, stream>>>(d_off, d_n_kept, n_neighbors, d_nbr, d_nbr_w,
+                                                                      d_nbr_cnt, eps, core, parent);
+  MODEST_LAUNCH_CHECK("dbscan_union_kernel");
+  dbscan_label_kernel<<<n_scans, 1024, 0, stream>>>(d_off, d_n_kept, d_kept_idx, n_neighbors, d_nbr, d_nbr_w,
+                                                    d_nbr_cnt, eps, core, parent, root_rank, d_labels_kept,
+                                                    d_labels_full, d_n_clusters);
+  MODEST_LAUNCH_CHECK("dbscan_label_kernel");
+  note_launch(3);
+  return MODEST_OK;
+}

@@ -9,160 +9,10 @@
 // radius.  Distances are decided in f32 when they are clear of the sphere surface and
 // re-evaluated in sequential f64 (the arithmetic of cKDTree) inside a thin shell around it, so
 // counts are bit-exact.  A last kernel turns the (N,T) counts into the normalised entropy.
-#include "common.cuh"
+#include "grid2d.cuh"
 
 namespace modest {
 extern void note_launch(int n);
-
-struct PPScanMeta {      // per scan, device resident
-  float x0, y0;          // grid origin
-  float inv_cell;        // 1 / cell edge
-  int   pad;
-};
-
-__device__ __forceinline__ int cell_coord(float v, float origin, float inv_cell) {
-  // monotone in v (one rounded subtract, one rounded multiply, floor) -- that is all the
-  // neighbour search needs; see DESIGN.md for the |cell(q) - cell(h)| <= 1 argument.
-  return __float2int_rd(__fmul_rn(__fsub_rn(v, origin), inv_cell));
-}
-// ints per scan in the cell table: G*G cells + sentinel, padded so every scan stays 16-B aligned
-__host__ __device__ __forceinline__ size_t cell_stride(int G) { return (size_t)G * G + 4; }
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
-// ---- 1. per-scan query bounding box -> grid origin -------------------------------------------
-__global__ void __launch_bounds__(1024) pp_query_origin_kernel(
-    const float* __restrict__ q_xyz, const int64_t* __restrict__ q_off, PPScanMeta* __restrict__ meta,
-    int G, float cell) {
-  const int s = blockIdx.x;
-  const int64_t beg = q_off[s], end = q_off[s + 1];
-  float lox = 3.0e38f, loy = 3.0e38f, hix = -3.0e38f, hiy = -3.0e38f;
-  for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
-    float x = q_xyz[3 * i], y = q_xyz[3 * i + 1];
-    lox = fminf(lox, x); hix = fmaxf(hix, x);
-    loy = fminf(loy, y); hiy = fmaxf(hiy, y);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o));
-    loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o));
-    hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
-    hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
-  }
-  __shared__ float sh[4][32];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { sh[0][w] = lox; sh[1][w] = loy; sh[2][w] = hix; sh[3][w] = hiy; }
-  __syncthreads();
-  if (w == 0) {
-    const int nw = blockDim.x >> 5;
-    lox = l < nw ? sh[0][l] : 3.0e38f;  loy = l < nw ? sh[1][l] : 3.0e38f;
-    hix = l < nw ? sh[2][l] : -3.0e38f; hiy = l < nw ? sh[3][l] : -3.0e38f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o));
-      loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o));
-      hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
-      hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
-    }
-    if (l == 0) {
-      PPScanMeta m;
-      if (end <= beg) { lox = loy = hix = hiy = 0.f; }
-      const float half = 0.5f * cell * (float)G;
-      m.x0 = 0.5f * (lox + hix) - half;
-      m.y0 = 0.5f * (loy + hiy) - half;
-      m.inv_cell = 1.0f / cell;
-      m.pad = 0;
-      meta[s] = m;
-    }
-  }
-}
-
-// ---- 2. histogram of query points per cell ---------------------------------------------------
-__global__ void __launch_bounds__(256) pp_query_hist_kernel(
-    const float* __restrict__ q_xyz, const int64_t* __restrict__ q_off,
-    const PPScanMeta* __restrict__ meta, int* __restrict__ cells, int G) {
-  const int s = blockIdx.y;
-  const int64_t beg = q_off[s], n = q_off[s + 1] - beg;
-  const PPScanMeta m = meta[s];
-  int* c = cells + (size_t)s * cell_stride(G);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float* p = q_xyz + 3 * (beg + i);
-    int cx = clampi(cell_coord(p[0], m.x0, m.inv_cell), 0, G - 1);
-    int cy = clampi(cell_coord(p[1], m.y0, m.inv_cell), 0, G - 1);
-    atomicAdd(&c[cy * G + cx], 1);
-  }
-}
-
-// ---- 3. in-place inclusive scan of the G*G cell counts, one CTA per scan ---------------------
-__global__ void __launch_bounds__(1024) pp_cell_scan_kernel(int* __restrict__ cells, int G) {
-  const size_t ncell = (size_t)G * G;
-  int* c = cells + (size_t)blockIdx.x * (ncell + 1);
-  __shared__ int warp_excl[32];
-  __shared__ int tile_total;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int carry = 0;                       // running prefix, identical in every thread
-  for (size_t base = 0; base < ncell; base += 4096) {
-    const size_t i = base + 4 * (size_t)threadIdx.x;
-    int4 v = make_int4(0, 0, 0, 0);
-    if (i + 3 < ncell) v = *reinterpret_cast<const int4*>(c + i);
-    else {
-      if (i < ncell) v.x = c[i];
-      if (i + 1 < ncell) v.y = c[i + 1];
-      if (i + 2 < ncell) v.z = c[i + 2];
-    }
-    v.y += v.x; v.z += v.y; v.w += v.z;
-    int incl = v.w;                    // inclusive scan of per-thread totals within the warp
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_excl[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-      const int t = warp_excl[lane];
-      int ti = t;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int u = __shfl_up_sync(0xffffffffu, ti, o);
-        if (lane >= o) ti += u;
-      }
-      warp_excl[lane] = ti - t;
-      if (lane == 31) tile_total = ti;
-    }
-    __syncthreads();
-    const int off = carry + warp_excl[w] + (incl - v.w);
-    v.x += off; v.y += off; v.z += off; v.w += off;
-    if (i + 3 < ncell) *reinterpret_cast<int4*>(c + i) = v;
-    else {
-      if (i < ncell) c[i] = v.x;
-      if (i + 1 < ncell) c[i + 1] = v.y;
-      if (i + 2 < ncell) c[i + 2] = v.z;
-    }
-    carry += tile_total;
-    __syncthreads();                   // warp_excl / tile_total are rewritten next tile
-  }
-  if (threadIdx.x == 0) c[ncell] = carry;   // sentinel: total number of query points
-}
-
-// ---- 4. scatter query points into cell order (x,y,z,original index) --------------------------
-__global__ void __launch_bounds__(256) pp_query_scatter_kernel(
-    const float* __restrict__ q_xyz, const int64_t* __restrict__ q_off,
-    const PPScanMeta* __restrict__ meta, int* __restrict__ cells, float4* __restrict__ sorted, int G) {
-  const int s = blockIdx.y;
-  const int64_t beg = q_off[s], n = q_off[s + 1] - beg;
-  const PPScanMeta m = meta[s];
-  int* c = cells + (size_t)s * cell_stride(G);
-  float4* out = sorted + beg;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float* p = q_xyz + 3 * (beg + i);
-    const float x = p[0], y = p[1], z = p[2];
-    int cx = clampi(cell_coord(x, m.x0, m.inv_cell), 0, G - 1);
-    int cy = clampi(cell_coord(y, m.y0, m.inv_cell), 0, G - 1);
-    // the scanned array holds the END of each cell; counting down leaves the START behind
-    int pos = atomicSub(&c[cy * G + cx], 1) - 1;
-    out[pos] = make_float4(x, y, z, __int_as_float((int)i));
-  }
-}
 
 // ---- 5. stream the history once: probe 3 row segments, count hits ----------------------------
 // blockIdx.y = global traversal index g; the scan it belongs to comes from trav_scan[g].
@@ -170,7 +20,7 @@ __global__ void __launch_bounds__(256) pp_count_kernel(
     const float* __restrict__ h_xyz, const int64_t* __restrict__ h_off,
     const int32_t* __restrict__ trav_scan, const int32_t* __restrict__ trav_off,
     const int64_t* __restrict__ q_off, const int64_t* __restrict__ count_off,
-    const PPScanMeta* __restrict__ meta, const int* __restrict__ cells,
+    const GridMeta* __restrict__ meta, const int* __restrict__ cells,
     const float4* __restrict__ sorted, int* __restrict__ counts, int G, float r2f, float band,
     double r2) {
   const int g = blockIdx.y;
@@ -178,7 +28,7 @@ __global__ void __launch_bounds__(256) pp_count_kernel(
   const int t = g - trav_off[s];
   const int T = trav_off[s + 1] - trav_off[s];
   const int64_t hbeg = h_off[g], hn = h_off[g + 1] - hbeg;
-  const PPScanMeta m = meta[s];
+  const GridMeta m = meta[s];
   const int* __restrict__ c = cells + (size_t)s * cell_stride(G);
   const float4* __restrict__ qs = sorted + q_off[s];
   int* __restrict__ cnt = counts + count_off[s] + t;
@@ -259,6 +109,35 @@ __global__ void pp_trav_scan_kernel(const int32_t* __restrict__ trav_off, int n_
   for (int g = trav_off[s] + threadIdx.x; g < trav_off[s + 1]; g += blockDim.x) trav_scan[g] = s;
 }
 
+
+// ---- stage B: rigid transform of scan frames into the fixed frame ------------------------------
+// transform_points() (utils/pointcloud_utils.py:11-19) is [p,1] @ Tr^T in float32 through
+// BLAS sgemm; its kernels accumulate the 4-term dot product with fused multiply-adds in k
+// order, which is what this kernel does.  remove_center() (pre_compute_pp_score.py:48-52) is
+// folded in: a removed point becomes NaN, which no distance test can ever accept.
+__global__ void __launch_bounds__(256) transform_frames_kernel(
+    const float* __restrict__ in, int stride, const int64_t* __restrict__ frame_off, const float* __restrict__ T,
+    int remove_center, float cx0, float cx1, float cy0, float cy1, float* __restrict__ out) {
+  const int f = blockIdx.y;
+  const int64_t beg = frame_off[f], n = frame_off[f + 1] - beg;
+  float t[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) t[k] = T[16 * f + k];
+  const float nanv = __int_as_float(0x7fc00000);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* p = in + (size_t)stride * (beg + i);
+    const float x = p[0], y = p[1], z = p[2];
+    float* o = out + 3 * (beg + i);
+    if (remove_center && x < cx1 && x >= cx0 && y < cy1 && y >= cy0) {
+      o[0] = nanv; o[1] = nanv; o[2] = nanv;
+      continue;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      o[j] = fmaf(1.0f, t[4 * j + 3], fmaf(z, t[4 * j + 2], fmaf(y, t[4 * j + 1], __fmul_rn(x, t[4 * j]))));
+  }
+}
+
 }  // namespace modest
 
 using namespace modest;
@@ -270,7 +149,7 @@ extern "C" size_t modest_pp_workspace_bytes(int n_scans, int64_t n_query_total, 
   if (grid_dim <= 0) grid_dim = 512;
   size_t b = 0;
   auto add = [&](size_t bytes) { b = align_up(b, 256) + bytes; };
-  add(sizeof(PPScanMeta) * (size_t)n_scans);
+  add(sizeof(GridMeta) * (size_t)n_scans);
   add(sizeof(int) * (size_t)n_scans * cell_stride(grid_dim));
   add(sizeof(float4) * (size_t)n_query_total);
   add(sizeof(int) * (size_t)n_count_total);
@@ -302,7 +181,7 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
   const int G = grid_dim;
   const size_t ncell1 = cell_stride(G);
   Arena ar(d_ws, ws_bytes);
-  PPScanMeta* meta = ar.take<PPScanMeta>(n_scans);
+  GridMeta* meta = ar.take<GridMeta>(n_scans);
   int* cells = ar.take<int>((size_t)n_scans * ncell1);
   float4* sorted = ar.take<float4>(n_query_total);
   int* counts_ws = ar.take<int>(n_count_total);
@@ -314,21 +193,17 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
   const float r2f = (float)r2;
   const float band = 1e-5f * r2f;   // ~100x the f32 evaluation error of d2 for d2 ~ r2
 
-  MODEST_CUDA(cudaMemsetAsync(cells, 0, sizeof(int) * (size_t)n_scans * ncell1, stream));
   MODEST_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)n_count_total, stream));
 
   pp_trav_scan_kernel<<<n_scans, 32, 0, stream>>>(d_trav_off, n_scans, trav_scan);
   MODEST_LAUNCH_CHECK("pp_trav_scan_kernel");
-  pp_query_origin_kernel<<<n_scans, 1024, 0, stream>>>(d_query_xyz, d_q_off, meta, G, cell);
-  MODEST_LAUNCH_CHECK("pp_query_origin_kernel");
+  {
+    int rc = grid2d_build(d_query_xyz, 3, d_q_off, nullptr, n_scans, max_query_points, cell, G, meta, cells,
+                          sorted, stream);
+    if (rc != MODEST_OK) return rc;
+  }
   const int qblocks = (int)((max_query_points + 255) / 256);
   dim3 qgrid(qblocks > 0 ? qblocks : 1, n_scans);
-  pp_query_hist_kernel<<<qgrid, 256, 0, stream>>>(d_query_xyz, d_q_off, meta, cells, G);
-  MODEST_LAUNCH_CHECK("pp_query_hist_kernel");
-  pp_cell_scan_kernel<<<n_scans, 1024, 0, stream>>>(cells, G);
-  MODEST_LAUNCH_CHECK("pp_cell_scan_kernel");
-  pp_query_scatter_kernel<<<qgrid, 256, 0, stream>>>(d_query_xyz, d_q_off, meta, cells, sorted, G);
-  MODEST_LAUNCH_CHECK("pp_query_scatter_kernel");
   if (n_trav_total > 0 && max_trav_points > 0) {
     int64_t hb = (max_trav_points + 255) / 256;
     if (hb > 65535) hb = 65535;
@@ -341,6 +216,27 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
   MODEST_REQUIRE(n_scans <= 65535, "pp_score: more than 65535 scans in one launch");
   pp_entropy_kernel<<<qgrid, 256, 0, stream>>>(counts, d_q_off, d_count_off, d_trav_off, d_pp);
   MODEST_LAUNCH_CHECK("pp_entropy_kernel");
-  note_launch(7);
+  note_launch(3);
+  return MODEST_OK;
+}
+
+extern "C" int modest_transform_frames_batch(const float* d_in, int point_stride, const int64_t* d_frame_off,
+                                             const float* d_T, int n_frames, int64_t max_frame_points,
+                                             int remove_center, const float* h_center_box, float* d_out,
+                                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_frames <= 0 || max_frame_points <= 0) return MODEST_OK;
+  MODEST_REQUIRE(d_in && d_frame_off && d_T && d_out, "transform_frames: null pointer argument");
+  MODEST_REQUIRE(point_stride >= 3, "transform_frames: point_stride %d < 3", point_stride);
+  MODEST_REQUIRE(n_frames <= 65535, "transform_frames: more than 65535 frames in one launch");
+  MODEST_REQUIRE(!remove_center || h_center_box, "transform_frames: remove_center without a box");
+  int64_t blocks = (max_frame_points + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  const float* c = h_center_box;
+  transform_frames_kernel<<<dim3((unsigned)blocks, n_frames), 256, 0, stream>>>(
+      d_in, point_stride, d_frame_off, d_T, remove_center, c ? c[0] : 0.f, c ? c[1] : 0.f, c ? c[2] : 0.f,
+      c ? c[3] : 0.f, d_out);
+  MODEST_LAUNCH_CHECK("transform_frames_kernel");
+  note_launch(1);
   return MODEST_OK;
 }

@@ -240,10 +240,13 @@ def sample_frame(world: World, pose: Pose, shape: Shape, rng, n_dynamic=(10, 30)
     pts_l = (np.concatenate([pts_w, np.ones((len(pts_w), 1))], 1) @ W2L.T)[:, :3]
     # trim / pad to exactly N (the dynamic share can overshoot by the 150-point floor)
     if len(pts_l) > N:
-        keep = np.ones(len(pts_l), bool)
-        drop = rng.choice(n_ground, len(pts_l) - N, replace=False)
-        keep[drop] = False
-        pts_l = pts_l[keep]
+        if len(pts_l) - N <= n_ground:
+            keep = np.ones(len(pts_l), bool)
+            drop = rng.choice(n_ground, len(pts_l) - N, replace=False)
+            keep[drop] = False
+            pts_l = pts_l[keep]
+        else:                       # tiny clouds: the 150-point floor per box exceeds the budget
+            pts_l = pts_l[rng.permutation(len(pts_l))[:N]]
     elif len(pts_l) < N:
         extra = N - len(pts_l)
         pts_l = np.concatenate([pts_l, pts_l[:extra] + rng.normal(0, 0.05, (extra, 3))])

@@ -41,18 +41,48 @@ def build(verbose=False):
     return built_path()
 
 
-def load():
-    """Import the built module (None when it was never built)."""
-    p = built_path()
-    if p is None:
-        return None
+def _import_so(name, p):
     import importlib.util
     import torch  # noqa: F401
-    spec = importlib.util.spec_from_file_location("iou3d_nms_cuda", p)
+    spec = importlib.util.spec_from_file_location(name, p)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
 
 
+def load():
+    """Import the built CUDA module (None when it was never built).  Use its *_gpu functions
+    only: its boxes_iou_bev_cpu exits the process (see ref_cpu_binding.cpp)."""
+    p = built_path()
+    return None if p is None else _import_so("iou3d_nms_cuda", p)
+
+
+def cpu_built_path():
+    p = os.path.join(OUT, "cpu", "iou3d_ref_cpu.so")
+    return p if os.path.exists(p) else None
+
+
+def build_cpu(verbose=False):
+    """The reference's iou3d_cpu.cpp alone + oracle/ref_cpu_binding.cpp -> oracle/_ref/cpu/."""
+    if cpu_built_path():
+        return cpu_built_path()
+    if not os.path.isdir(SRC):
+        return None
+    out = os.path.join(OUT, "cpu")
+    os.makedirs(out, exist_ok=True)
+    from torch.utils import cpp_extension
+    cpp_extension.load(name="iou3d_ref_cpu",
+                       sources=[os.path.join(SRC, "iou3d_cpu.cpp"), os.path.join(HERE, "ref_cpu_binding.cpp")],
+                       extra_cflags=["-g"], extra_include_paths=["/usr/local/cuda/include"],
+                       build_directory=out, verbose=verbose, is_python_module=False)
+    return cpu_built_path()
+
+
+def load_cpu():
+    p = cpu_built_path()
+    return None if p is None else _import_so("iou3d_ref_cpu", p)
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv))
+    print(build_cpu(verbose="-v" in sys.argv))

@@ -64,17 +64,23 @@ def _install_stubs():
         sys.modules["omegaconf"] = oc
     if "pyquaternion" not in sys.modules:
         pq = types.ModuleType("pyquaternion")
-        from scipy.spatial.transform import Rotation
 
         class Quaternion:
+            """pyquaternion's axis-angle constructor and transformation_matrix, restated
+            (q-matrix times conjugate q-bar-matrix, rows/cols 1..3)."""
+
             def __init__(self, axis, angle):
                 ax = np.asarray(axis, float)
-                self._r = Rotation.from_rotvec(ax / np.linalg.norm(ax) * angle)
+                ax = ax / np.linalg.norm(ax)
+                self.q = np.concatenate([[np.cos(angle / 2.0)], ax * np.sin(angle / 2.0)])
 
             @property
             def transformation_matrix(self):
+                w, x, y, z = self.q
+                qm = np.array([[w, -x, -y, -z], [x, w, -z, y], [y, z, w, -x], [z, -y, x, w]])
+                qb = np.array([[w, -x, -y, -z], [x, w, z, -y], [y, -z, w, x], [z, y, -x, w]])
                 m = np.eye(4)
-                m[:3, :3] = self._r.as_matrix()
+                m[:3, :3] = np.dot(qm, qb.conj().transpose())[1:][:, 1:]
                 return m
 
         pq.Quaternion = Quaternion
@@ -110,9 +116,10 @@ def load():
         from utils import pointcloud_utils as ref_pc    # noqa
         from utils import clustering_utils as ref_cl    # noqa
         from utils import kitti_util as ref_ku          # noqa
+        import generate_mask as ref_gm                  # noqa
     finally:
         sys.path.remove(_GCM)
-    ns = types.SimpleNamespace(pp=ref_pp, pc=ref_pc, cl=ref_cl, ku=ref_ku, AttrDict=_AttrDict)
+    ns = types.SimpleNamespace(pp=ref_pp, pc=ref_pc, cl=ref_cl, ku=ref_ku, gm=ref_gm, AttrDict=_AttrDict)
     # keep the reference's `utils` package from shadowing anything of ours
     ns._mods = {k: sys.modules.pop(k) for k in list(sys.modules)
                 if k == "utils" or k.startswith("utils.")}
