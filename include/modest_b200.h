@@ -92,6 +92,14 @@ int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_q_off,
                           int grid_dim, int32_t* d_counts, const int64_t* d_count_off,
                           float* d_pp, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Timing hook for the dominant kernel (pp_count_kernel): with n_slots > 0 every
+ * modest_pp_score_batch call records a CUDA event pair around that kernel on the launching
+ * stream, in a ring of n_slots pairs (n_slots = 0 switches it off).  After synchronising the
+ * stream, modest_pp_profile_read writes the durations [ms] of the most recent launches
+ * (newest first) into h_ms and returns how many it wrote. */
+int modest_pp_profile_enable(int n_slots);
+int modest_pp_profile_read(float* h_ms, int max_out);
+
 /* ------------------------------------------------------------------------------------------
  * Stage E: RANSAC ground plane.
  * Replaces estimate_plane() (utils/pointcloud_utils.py:44-65), i.e. sklearn's

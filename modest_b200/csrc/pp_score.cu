@@ -142,6 +142,34 @@ __global__ void __launch_bounds__(256) transform_frames_kernel(
 
 using namespace modest;
 
+// ---- optional timing of the dominant kernel (bench.py's roofline line) ---------------------------
+// A ring of CUDA event pairs recorded on the launching stream around pp_count_kernel; read back
+// after the caller has synchronised.  Off by default.
+static cudaEvent_t g_prof_ev[2 * 256];
+static int g_prof_slots = 0;
+static long long g_prof_calls = 0;
+
+extern "C" int modest_pp_profile_enable(int n_slots) {
+  if (n_slots < 0 || n_slots > 256) { set_error("pp_profile_enable: n_slots %d out of range [0,256]", n_slots); return MODEST_ERR_ARG; }
+  for (int i = 0; i < 2 * g_prof_slots; ++i) cudaEventDestroy(g_prof_ev[i]);
+  g_prof_slots = 0;
+  g_prof_calls = 0;
+  for (int i = 0; i < 2 * n_slots; ++i) MODEST_CUDA(cudaEventCreate(&g_prof_ev[i]));
+  g_prof_slots = n_slots;
+  return MODEST_OK;
+}
+
+// ms per recorded pp_count launch (most recent min(calls, slots)); returns the number written
+extern "C" int modest_pp_profile_read(float* h_ms, int max_out) {
+  int n = (int)(g_prof_calls < g_prof_slots ? g_prof_calls : g_prof_slots);
+  if (n > max_out) n = max_out;
+  for (int i = 0; i < n; ++i) {
+    const int slot = (int)((g_prof_calls - 1 - i) % g_prof_slots);
+    if (cudaEventElapsedTime(&h_ms[i], g_prof_ev[2 * slot], g_prof_ev[2 * slot + 1]) != cudaSuccess) { h_ms[i] = -1.f; cudaGetLastError(); }
+  }
+  return n;
+}
+
 static const float kCellSlack = 1.001f;   // cell edge = radius * slack, see cell_coord()
 
 extern "C" size_t modest_pp_workspace_bytes(int n_scans, int64_t n_query_total, int64_t n_count_total,
@@ -209,9 +237,12 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
     if (hb > 65535) hb = 65535;
     dim3 hgrid((unsigned)hb, n_trav_total);
     MODEST_REQUIRE(n_trav_total <= 65535, "pp_score: more than 65535 traversals in one launch");
+    const int slot = g_prof_slots ? (int)(g_prof_calls % g_prof_slots) : -1;
+    if (slot >= 0) cudaEventRecord(g_prof_ev[2 * slot], stream);
     pp_count_kernel<<<hgrid, 256, 0, stream>>>(d_hist_xyz, d_h_off, trav_scan, d_trav_off, d_q_off,
                                                d_count_off, meta, cells, sorted, counts, G, r2f, band, r2);
     MODEST_LAUNCH_CHECK("pp_count_kernel");
+    if (slot >= 0) { cudaEventRecord(g_prof_ev[2 * slot + 1], stream); ++g_prof_calls; }
   }
   MODEST_REQUIRE(n_scans <= 65535, "pp_score: more than 65535 scans in one launch");
   pp_entropy_kernel<<<qgrid, 256, 0, stream>>>(counts, d_q_off, d_count_off, d_trav_off, d_pp);
