@@ -268,18 +268,87 @@ __device__ __forceinline__ void project(double x, double z, double c, double s, 
 }
 
 constexpr int kFitThreads = 256;
+constexpr int kCandCap = 64;            // f64 re-scoring handles at most this many near-maximal angles
+constexpr float kBetaMargin = 5e-3f;    // >> 2x the relative error of the float32 pre-pass
+constexpr int kAngleChunks = 8;         // the pre-pass splits the 901 angles over this many CTAs per cluster
+constexpr int kPrepassCap = 4096;       // cluster points cached in shared memory by the pre-pass
+
+// ---- L.0 float32 pre-pass of the closeness score over all search angles -------------------------
+// grid (cluster slots, kAngleChunks, scans).  Coordinates are centred on the cluster's first
+// point in f64 before the cast, so float32 keeps ~1e-6 m accuracy whatever the range.
+__global__ void __launch_bounds__(256) box_beta32_kernel(
+    const int64_t* __restrict__ off, const double* __restrict__ rect, int max_clusters, const int32_t* __restrict__ n_clusters,
+    const ClusterStat* __restrict__ stats, const int32_t* __restrict__ cl_off, const int32_t* __restrict__ members,
+    const double* __restrict__ trig, int n_angles, float d0, const int32_t* __restrict__ new_id,
+    const int32_t* __restrict__ has_noise, float* __restrict__ beta32, int max_valid) {
+  const int s = blockIdx.z;
+  const int C = min(n_clusters[s], max_clusters);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __shared__ float2 pts[kPrepassCap];
+  const int per = (n_angles + kAngleChunks - 1) / kAngleChunks;
+  const int a0 = blockIdx.y * per, a1 = min(n_angles, a0 + per);
+  const double* R = rect + 3 * off[s];
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    const ClusterStat* st = stats + (size_t)s * max_clusters + c;
+    if (!st->valid) continue;
+    const int rank = new_id[(size_t)s * max_clusters + c] - has_noise[s];
+    if (rank < 0 || rank >= max_valid) continue;
+    const int n = st->count;
+    const int32_t* mem = members + off[s] + cl_off[(size_t)s * (max_clusters + 1) + c];
+    const double x0 = R[3 * mem[0]], z0 = R[3 * mem[0] + 2];
+    __syncthreads();
+    for (int i = threadIdx.x; i < min(n, kPrepassCap); i += blockDim.x) {
+      const int m = mem[i];
+      pts[i] = make_float2((float)(R[3 * m] - x0), (float)(R[3 * m + 2] - z0));
+    }
+    __syncthreads();
+    auto point = [&](int i) {
+      if (i < kPrepassCap) return pts[i];
+      const int m = mem[i];
+      return make_float2((float)(R[3 * m] - x0), (float)(R[3 * m + 2] - z0));
+    };
+    float* out = beta32 + ((size_t)s * max_valid + rank) * n_angles;
+    for (int a = a0 + w; a < a1; a += nw) {
+      const float cs = (float)trig[a], sn = (float)trig[n_angles + a];
+      float lox = 3e38f, hix = -3e38f, loy = 3e38f, hiy = -3e38f;
+      for (int i = lane; i < n; i += 32) {
+        const float2 p = point(i);
+        const float px = fmaf(p.y, sn, p.x * cs), py = fmaf(p.y, cs, -p.x * sn);
+        lox = fminf(lox, px); hix = fmaxf(hix, px); loy = fminf(loy, py); hiy = fmaxf(hiy, py);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+        loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+      }
+      float beta = 0.f;
+      for (int i = lane; i < n; i += 32) {
+        const float2 p = point(i);
+        const float px = fmaf(p.y, sn, p.x * cs), py = fmaf(p.y, cs, -p.x * sn);
+        const float dx = fminf(px - lox, hix - px), dy = fminf(py - loy, hiy - py);
+        beta += __frcp_rn(fmaxf(fminf(dx, dy), d0));
+      }
+      beta = warp_sum(beta);
+      if (lane == 0) out[a] = beta;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kFitThreads) box_fit_kernel(
     const int64_t* __restrict__ off, const double* __restrict__ rect, int max_clusters, const int32_t* __restrict__ n_clusters,
     const ClusterStat* __restrict__ stats, const int32_t* __restrict__ cl_off, const int32_t* __restrict__ members,
     const double* __restrict__ trig /* (4, n_angles): cos, sin, cos(+pi/2), sin(+pi/2) */, int n_angles,
-    const double* __restrict__ angles /* (2, n_angles): angle, angle+pi/2 */, double d0, BoxRec* __restrict__ boxes) {
+    const double* __restrict__ angles /* (2, n_angles): angle, angle+pi/2 */, double d0, BoxRec* __restrict__ boxes,
+    const int32_t* __restrict__ new_id, const int32_t* __restrict__ has_noise, const float* __restrict__ beta32,
+    int max_valid) {
   const int s = blockIdx.y;
   const int C = min(n_clusters[s], max_clusters);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = kFitThreads / 32;
   __shared__ double sh_beta[kFitThreads / 32];
   __shared__ int sh_idx[kFitThreads / 32];
   __shared__ double sh_red[4][kFitThreads / 32];
+  __shared__ int sh_ncand;
+  __shared__ int sh_cand[kCandCap];
   for (int c = blockIdx.x; c < C; c += gridDim.x) {
     const ClusterStat* st = stats + (size_t)s * max_clusters + c;
     BoxRec* bx = boxes + (size_t)s * max_clusters + c;
@@ -287,10 +356,9 @@ __global__ void __launch_bounds__(kFitThreads) box_fit_kernel(
     const int n = st->count;
     const int32_t* mem = members + off[s] + cl_off[(size_t)s * (max_clusters + 1) + c];
     const double* R = rect + 3 * off[s];
-    // ---- heading search: each warp scans a strided subset of the angles ----
-    double best_beta = -1e300;
-    int best_idx = 0x7fffffff;
-    for (int a = w; a < n_angles; a += nw) {
+    // ---- heading search -----------------------------------------------------------------
+    // beta64(a): the reference's score at search angle a, f64, one warp
+    auto beta64 = [&](int a) {
       const double cs = trig[a], sn = trig[n_angles + a];
       double lox = 1e300, hix = -1e300, loy = 1e300, hiy = -1e300;
       for (int i = lane; i < n; i += 32) {
@@ -309,9 +377,52 @@ __global__ void __launch_bounds__(kFitThreads) box_fit_kernel(
         const double dy = fmin(__dsub_rn(py, loy), __dsub_rn(hiy, py));
         beta += __ddiv_rn(1.0, fmax(fmin(dx, dy), d0));
       }
-      beta = warp_sum(beta);
-      if (beta > best_beta) { best_beta = beta; best_idx = a; }   // ascending a: first strict max wins
+      return warp_sum(beta);
+    };
+    double best_beta = -1e300;
+    int best_idx = 0x7fffffff;
+    // The float32 pre-pass (box_beta32_kernel) scored every angle; only angles whose f32 score is
+    // within kBetaMargin of the f32 maximum can hold the f64 maximum (the f32 evaluation error is
+    // far below the margin), so only those are re-scored in f64.  Falls back to the full f64
+    // scan when the cluster has no pre-pass slot or too many angles are that close.
+    const int rank = new_id[(size_t)s * max_clusters + c] - has_noise[s];
+    bool full_scan = !(beta32 && rank >= 0 && rank < max_valid);
+    if (!full_scan) {
+      const float* b32 = beta32 + ((size_t)s * max_valid + rank) * n_angles;
+      float m32 = -3.0e38f;
+      for (int a = threadIdx.x; a < n_angles; a += kFitThreads) m32 = fmaxf(m32, b32[a]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m32 = fmaxf(m32, __shfl_xor_sync(0xffffffffu, m32, o));
+      __syncthreads();
+      if (threadIdx.x == 0) sh_ncand = 0;
+      if (lane == 0) sh_red[0][w] = (double)m32;
+      __syncthreads();
+      float mx = (float)sh_red[0][0];
+      for (int k = 1; k < nw; ++k) mx = fmaxf(mx, (float)sh_red[0][k]);
+      const float thr = mx * (1.0f - kBetaMargin);
+      for (int a = threadIdx.x; a < n_angles; a += kFitThreads)
+        if (b32[a] >= thr) {
+          const int k = atomicAdd(&sh_ncand, 1);
+          if (k < kCandCap) sh_cand[k] = a;
+        }
+      __syncthreads();
+      const int nc = sh_ncand;
+      if (nc > kCandCap || nc == 0) full_scan = true;      // block-uniform
+      else
+        for (int ci = w; ci < nc; ci += nw) {
+          const int a = sh_cand[ci];
+          const double beta = beta64(a);
+          if (beta > best_beta || (beta == best_beta && a < best_idx)) { best_beta = beta; best_idx = a; }
+        }
     }
+    if (full_scan) {
+      best_beta = -1e300; best_idx = 0x7fffffff;
+      for (int a = w; a < n_angles; a += nw) {
+        const double beta = beta64(a);
+        if (beta > best_beta) { best_beta = beta; best_idx = a; }   // ascending a: first strict max wins
+      }
+    }
+    __syncthreads();
     if (lane == 0) { sh_beta[w] = best_beta; sh_idx[w] = best_idx; }
     __syncthreads();
     int sel = 0;
@@ -495,6 +606,9 @@ __global__ void __launch_bounds__(256) apply_final_kernel(const int64_t* __restr
 
 using namespace modest;
 
+static const int kMaxAngles = 1024;
+static int prepass_slots(int max_clusters) { return max_clusters < 384 ? max_clusters : 384; }
+
 extern "C" size_t modest_filter_workspace_bytes(int n_scans, int64_t n_points_total, int max_clusters) {
   size_t b = 0;
   auto add = [&](size_t bytes) { b = align_up(b, 256) + bytes; };
@@ -509,6 +623,7 @@ extern "C" size_t modest_filter_workspace_bytes(int n_scans, int64_t n_points_to
   add(sizeof(unsigned long long) * (size_t)n_scans * max_clusters);   // bottom
   add(sizeof(int32_t) * (size_t)n_scans * (max_clusters + 1));   // final_id
   add(sizeof(CalibDev) * (size_t)n_scans);
+  add(sizeof(float) * (size_t)n_scans * prepass_slots(max_clusters) * kMaxAngles);   // beta32
   return b + 256;
 }
 
@@ -543,6 +658,8 @@ extern "C" int modest_filter_and_fit_batch(
   unsigned long long* bottom = ar.take<unsigned long long>((size_t)n_scans * max_clusters);
   int32_t* final_id = ar.take<int32_t>((size_t)n_scans * (max_clusters + 1));
   CalibDev* calibs = ar.take<CalibDev>(n_scans);
+  const int max_valid = prepass_slots(max_clusters);
+  float* beta32 = ar.take<float>((size_t)n_scans * max_valid * kMaxAngles);
   int32_t* has_noise = nv_hn + n_scans;
 
   FilterCfg fc;
@@ -582,8 +699,15 @@ extern "C" int modest_filter_and_fit_batch(
     rect_coords_kernel<<<pgrid, 256, 0, stream>>>(d_ptc, point_stride, d_off, calibs, rect_ws);
     MODEST_LAUNCH_CHECK("rect_coords_kernel");
   }
+  MODEST_REQUIRE(n_angles <= kMaxAngles, "filter_and_fit: more than %d search angles", kMaxAngles);
+  // beta32 rows are n_angles wide (n_angles <= kMaxAngles, the stride the workspace was sized for)
+  box_beta32_kernel<<<dim3(cblocks, kAngleChunks, n_scans), 256, 0, stream>>>(d_off, rect, max_clusters, d_n_clusters, stats, cl_off,
+                                                                           members, d_trig, n_angles, (float)d0, new_id, has_noise,
+                                                                           beta32, max_valid);
+  MODEST_LAUNCH_CHECK("box_beta32_kernel");
   box_fit_kernel<<<dim3(cblocks, n_scans), kFitThreads, 0, stream>>>(d_off, rect, max_clusters, d_n_clusters, stats, cl_off, members,
-                                                                   d_trig, n_angles, d_angles, d0, boxes);
+                                                                   d_trig, n_angles, d_angles, d0, boxes, new_id, has_noise, beta32,
+                                                                   max_valid);
   MODEST_LAUNCH_CHECK("box_fit_kernel");
   box_bottom_kernel<<<pgrid, 256, 0, stream>>>(d_off, rect, max_clusters, d_n_clusters, stats, boxes, bottom);
   MODEST_LAUNCH_CHECK("box_bottom_kernel");
@@ -592,6 +716,6 @@ extern "C" int modest_filter_and_fit_batch(
   MODEST_LAUNCH_CHECK("box_finalize_kernel");
   apply_final_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_labels_filtered, max_clusters, final_id, d_labels_final);
   MODEST_LAUNCH_CHECK("apply_final_kernel");
-  note_launch(12);
+  note_launch(13);
   return MODEST_OK;
 }
