@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(256) cluster_validate_kernel(
 // ---- J.4 relabel: valid clusters -> 1..K in id order (0 = everything else) --------------------
 __global__ void cluster_relabel_kernel(const int64_t* __restrict__ off, int max_clusters, const int32_t* __restrict__ n_clusters,
                                        const ClusterStat* __restrict__ stats, int32_t* __restrict__ new_id /* (S,max_clusters) */,
-                                       int32_t* __restrict__ n_valid, int32_t* __restrict__ has_noise, int n_scans) {
+                                       int32_t* __restrict__ n_valid, int32_t* __restrict__ has_noise, int n_scans,
+                                       int32_t* __restrict__ valid_list /* (S,max_valid) cluster id per rank */, int max_valid) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_scans) return;
   const int C = min(n_clusters[s], max_clusters);
@@ -203,7 +204,11 @@ __global__ void cluster_relabel_kernel(const int64_t* __restrict__ off, int max_
   const int noise = covered < n ? 1 : 0;
   int k = 0;
   for (int c = 0; c < C; ++c) {
-    if (st[c].valid) { new_id[(size_t)s * max_clusters + c] = k + noise; ++k; }
+    if (st[c].valid) {
+      new_id[(size_t)s * max_clusters + c] = k + noise;
+      if (k < max_valid) valid_list[(size_t)s * max_valid + k] = c;
+      ++k;
+    }
     else new_id[(size_t)s * max_clusters + c] = noise ? 0 : -1;
   }
   n_valid[s] = k;
@@ -270,67 +275,66 @@ __device__ __forceinline__ void project(double x, double z, double c, double s, 
 constexpr int kFitThreads = 256;
 constexpr int kCandCap = 64;            // f64 re-scoring handles at most this many near-maximal angles
 constexpr float kBetaMargin = 5e-3f;    // >> 2x the relative error of the float32 pre-pass
-constexpr int kAngleChunks = 8;         // the pre-pass splits the 901 angles over this many CTAs per cluster
-constexpr int kPrepassCap = 4096;       // cluster points cached in shared memory by the pre-pass
+constexpr int kAngleChunks = 15;        // the pre-pass splits the 901 angles over this many CTAs per cluster
 
 // ---- L.0 float32 pre-pass of the closeness score over all search angles -------------------------
-// grid (cluster slots, kAngleChunks, scans).  Coordinates are centred on the cluster's first
-// point in f64 before the cast, so float32 keeps ~1e-6 m accuracy whatever the range.
-__global__ void __launch_bounds__(256) box_beta32_kernel(
-    const int64_t* __restrict__ off, const double* __restrict__ rect, int max_clusters, const int32_t* __restrict__ n_clusters,
-    const ClusterStat* __restrict__ stats, const int32_t* __restrict__ cl_off, const int32_t* __restrict__ members,
-    const double* __restrict__ trig, int n_angles, float d0, const int32_t* __restrict__ new_id,
-    const int32_t* __restrict__ has_noise, float* __restrict__ beta32, int max_valid) {
-  const int s = blockIdx.z;
-  const int C = min(n_clusters[s], max_clusters);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  __shared__ float2 pts[kPrepassCap];
-  const int per = (n_angles + kAngleChunks - 1) / kAngleChunks;
-  const int a0 = blockIdx.y * per, a1 = min(n_angles, a0 + per);
+// box_center32: member coordinates of every valid cluster, centred on the cluster's first point
+// in f64 and only then rounded, so float32 keeps ~1e-6 m accuracy whatever the range; stored
+// cluster-contiguously (same layout as `members`).
+__global__ void __launch_bounds__(256) box_center32_kernel(
+    const int64_t* __restrict__ off, const double* __restrict__ rect, int max_clusters, const ClusterStat* __restrict__ stats,
+    const int32_t* __restrict__ cl_off, const int32_t* __restrict__ members, const int32_t* __restrict__ n_valid,
+    const int32_t* __restrict__ valid_list, int max_valid, float2* __restrict__ xz32) {
+  const int s = blockIdx.z, rank = blockIdx.y;
+  if (rank >= min(n_valid[s], max_valid)) return;
+  const int c = valid_list[(size_t)s * max_valid + rank];
+  const int n = stats[(size_t)s * max_clusters + c].count;
+  const int64_t mbase = off[s] + cl_off[(size_t)s * (max_clusters + 1) + c];
+  const int32_t* mem = members + mbase;
   const double* R = rect + 3 * off[s];
-  for (int c = blockIdx.x; c < C; c += gridDim.x) {
-    const ClusterStat* st = stats + (size_t)s * max_clusters + c;
-    if (!st->valid) continue;
-    const int rank = new_id[(size_t)s * max_clusters + c] - has_noise[s];
-    if (rank < 0 || rank >= max_valid) continue;
-    const int n = st->count;
-    const int32_t* mem = members + off[s] + cl_off[(size_t)s * (max_clusters + 1) + c];
-    const double x0 = R[3 * mem[0]], z0 = R[3 * mem[0] + 2];
-    __syncthreads();
-    for (int i = threadIdx.x; i < min(n, kPrepassCap); i += blockDim.x) {
-      const int m = mem[i];
-      pts[i] = make_float2((float)(R[3 * m] - x0), (float)(R[3 * m + 2] - z0));
+  const double x0 = R[3 * mem[0]], z0 = R[3 * mem[0] + 2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int m = mem[i];
+    xz32[mbase + i] = make_float2((float)(R[3 * m] - x0), (float)(R[3 * m + 2] - z0));
+  }
+}
+
+// grid (kAngleChunks, valid-cluster rank, scan); each warp scores a strided subset of the chunk
+__global__ void __launch_bounds__(256) box_beta32_kernel(
+    const int64_t* __restrict__ off, int max_clusters, const ClusterStat* __restrict__ stats, const int32_t* __restrict__ cl_off,
+    const int32_t* __restrict__ n_valid, const int32_t* __restrict__ valid_list, int max_valid, const float2* __restrict__ xz32,
+    const double* __restrict__ trig, int n_angles, float d0, float* __restrict__ beta32) {
+  const int s = blockIdx.z, rank = blockIdx.y;
+  if (rank >= min(n_valid[s], max_valid)) return;
+  const int c = valid_list[(size_t)s * max_valid + rank];
+  const int n = stats[(size_t)s * max_clusters + c].count;
+  const float2* __restrict__ pts = xz32 + off[s] + cl_off[(size_t)s * (max_clusters + 1) + c];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int per = (n_angles + gridDim.x - 1) / gridDim.x;
+  const int a0 = blockIdx.x * per, a1 = min(n_angles, a0 + per);
+  float* out = beta32 + ((size_t)s * max_valid + rank) * n_angles;
+  for (int a = a0 + w; a < a1; a += nw) {
+    const float cs = (float)trig[a], sn = (float)trig[n_angles + a];
+    float lox = 3e38f, hix = -3e38f, loy = 3e38f, hiy = -3e38f;
+    for (int i = lane; i < n; i += 32) {
+      const float2 p = __ldg(pts + i);
+      const float px = fmaf(p.y, sn, p.x * cs), py = fmaf(p.y, cs, -p.x * sn);
+      lox = fminf(lox, px); hix = fmaxf(hix, px); loy = fminf(loy, py); hiy = fmaxf(hiy, py);
     }
-    __syncthreads();
-    auto point = [&](int i) {
-      if (i < kPrepassCap) return pts[i];
-      const int m = mem[i];
-      return make_float2((float)(R[3 * m] - x0), (float)(R[3 * m + 2] - z0));
-    };
-    float* out = beta32 + ((size_t)s * max_valid + rank) * n_angles;
-    for (int a = a0 + w; a < a1; a += nw) {
-      const float cs = (float)trig[a], sn = (float)trig[n_angles + a];
-      float lox = 3e38f, hix = -3e38f, loy = 3e38f, hiy = -3e38f;
-      for (int i = lane; i < n; i += 32) {
-        const float2 p = point(i);
-        const float px = fmaf(p.y, sn, p.x * cs), py = fmaf(p.y, cs, -p.x * sn);
-        lox = fminf(lox, px); hix = fmaxf(hix, px); loy = fminf(loy, py); hiy = fmaxf(hiy, py);
-      }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
-        loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
-      }
-      float beta = 0.f;
-      for (int i = lane; i < n; i += 32) {
-        const float2 p = point(i);
-        const float px = fmaf(p.y, sn, p.x * cs), py = fmaf(p.y, cs, -p.x * sn);
-        const float dx = fminf(px - lox, hix - px), dy = fminf(py - loy, hiy - py);
-        beta += __frcp_rn(fmaxf(fminf(dx, dy), d0));
-      }
-      beta = warp_sum(beta);
-      if (lane == 0) out[a] = beta;
+    for (int o = 16; o > 0; o >>= 1) {
+      lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+      loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
     }
+    float beta = 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const float2 p = __ldg(pts + i);
+      const float px = fmaf(p.y, sn, p.x * cs), py = fmaf(p.y, cs, -p.x * sn);
+      const float dx = fminf(px - lox, hix - px), dy = fminf(py - loy, hiy - py);
+      beta += __fdividef(1.0f, fmaxf(fminf(dx, dy), d0));
+    }
+    beta = warp_sum(beta);
+    if (lane == 0) out[a] = beta;
   }
 }
 
@@ -624,6 +628,8 @@ extern "C" size_t modest_filter_workspace_bytes(int n_scans, int64_t n_points_to
   add(sizeof(int32_t) * (size_t)n_scans * (max_clusters + 1));   // final_id
   add(sizeof(CalibDev) * (size_t)n_scans);
   add(sizeof(float) * (size_t)n_scans * prepass_slots(max_clusters) * kMaxAngles);   // beta32
+  add(sizeof(int32_t) * (size_t)n_scans * prepass_slots(max_clusters));              // valid_list
+  add(sizeof(float2) * (size_t)n_points_total);                                      // centred f32 member coords
   return b + 256;
 }
 
@@ -660,6 +666,8 @@ extern "C" int modest_filter_and_fit_batch(
   CalibDev* calibs = ar.take<CalibDev>(n_scans);
   const int max_valid = prepass_slots(max_clusters);
   float* beta32 = ar.take<float>((size_t)n_scans * max_valid * kMaxAngles);
+  int32_t* valid_list = ar.take<int32_t>((size_t)n_scans * max_valid);
+  float2* xz32 = ar.take<float2>(n_points_total);
   int32_t* has_noise = nv_hn + n_scans;
 
   FilterCfg fc;
@@ -691,7 +699,8 @@ extern "C" int modest_filter_and_fit_batch(
   const int cblocks = max_clusters < 512 ? max_clusters : 512;
   cluster_validate_kernel<<<dim3(cblocks, n_scans), 256, 0, stream>>>(d_off, d_pp, max_clusters, d_n_clusters, cl_off, members, fc, stats);
   MODEST_LAUNCH_CHECK("cluster_validate_kernel");
-  cluster_relabel_kernel<<<(n_scans + 63) / 64, 64, 0, stream>>>(d_off, max_clusters, d_n_clusters, stats, new_id, d_n_valid, has_noise, n_scans);
+  cluster_relabel_kernel<<<(n_scans + 63) / 64, 64, 0, stream>>>(d_off, max_clusters, d_n_clusters, stats, new_id, d_n_valid, has_noise, n_scans,
+                                                                valid_list, max_valid);
   MODEST_LAUNCH_CHECK("cluster_relabel_kernel");
   apply_relabel_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_labels, max_clusters, new_id, d_labels_filtered);
   MODEST_LAUNCH_CHECK("apply_relabel_kernel");
@@ -701,9 +710,11 @@ extern "C" int modest_filter_and_fit_batch(
   }
   MODEST_REQUIRE(n_angles <= kMaxAngles, "filter_and_fit: more than %d search angles", kMaxAngles);
   // beta32 rows are n_angles wide (n_angles <= kMaxAngles, the stride the workspace was sized for)
-  box_beta32_kernel<<<dim3(cblocks, kAngleChunks, n_scans), 256, 0, stream>>>(d_off, rect, max_clusters, d_n_clusters, stats, cl_off,
-                                                                           members, d_trig, n_angles, (float)d0, new_id, has_noise,
-                                                                           beta32, max_valid);
+  box_center32_kernel<<<dim3(4, max_valid, n_scans), 256, 0, stream>>>(d_off, rect, max_clusters, stats, cl_off, members, d_n_valid,
+                                                                      valid_list, max_valid, xz32);
+  MODEST_LAUNCH_CHECK("box_center32_kernel");
+  box_beta32_kernel<<<dim3(kAngleChunks, max_valid, n_scans), 256, 0, stream>>>(d_off, max_clusters, stats, cl_off, d_n_valid, valid_list,
+                                                                             max_valid, xz32, d_trig, n_angles, (float)d0, beta32);
   MODEST_LAUNCH_CHECK("box_beta32_kernel");
   box_fit_kernel<<<dim3(cblocks, n_scans), kFitThreads, 0, stream>>>(d_off, rect, max_clusters, d_n_clusters, stats, cl_off, members,
                                                                    d_trig, n_angles, d_angles, d0, boxes, new_id, has_noise, beta32,
@@ -716,6 +727,6 @@ extern "C" int modest_filter_and_fit_batch(
   MODEST_LAUNCH_CHECK("box_finalize_kernel");
   apply_final_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_labels_filtered, max_clusters, final_id, d_labels_final);
   MODEST_LAUNCH_CHECK("apply_final_kernel");
-  note_launch(13);
+  note_launch(14);
   return MODEST_OK;
 }

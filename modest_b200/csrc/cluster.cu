@@ -353,6 +353,8 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
   }
 }
 
+// one warp per core row: lanes sweep the row's (<= k) edges, each undirected core-core edge is
+// united once (from its larger endpoint)
 __global__ void __launch_bounds__(256) dbscan_union_kernel(
     const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, int k_nn, const int32_t* __restrict__ nbr,
     const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt, double eps, const uint8_t* __restrict__ core,
@@ -360,38 +362,35 @@ __global__ void __launch_bounds__(256) dbscan_union_kernel(
   const int s = blockIdx.y;
   const int n = n_kept[s];
   const int64_t base = off[s];
-  const int64_t total = (int64_t)n * k_nn;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(e / k_nn), c = (int)(e % k_nn);
-    if (c >= nbr_cnt[base + i] || !core[base + i]) continue;
-    const int j = nbr[(size_t)(base + i) * k_nn + c];
-    if (j >= i || !core[base + j]) continue;       // each undirected edge once
-    if ((double)nbr_w[(size_t)(base + i) * k_nn + c] <= eps) uf_union(parent + base, i, j);
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < n; i += nwarps) {
+    if (!core[base + i]) continue;                 // warp-uniform
+    const int m = nbr_cnt[base + i];
+    const size_t row = (size_t)(base + i) * k_nn;
+    for (int c = lane; c < m; c += 32) {
+      const int j = nbr[row + c];
+      if (j < i && core[base + j] && (double)nbr_w[row + c] <= eps) uf_union(parent + base, i, j);
+    }
   }
 }
 
-// One CTA per scan: number the clusters by their smallest core index (sklearn visits points in
-// index order), label cores, then borders (smallest cluster id among core neighbours), and
-// scatter into the full-size label array.
-__global__ void __launch_bounds__(1024) dbscan_label_kernel(
-    const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, const int32_t* __restrict__ kept_idx,
-    int k_nn, const int32_t* __restrict__ nbr, const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt,
-    double eps, const uint8_t* __restrict__ core, int32_t* __restrict__ parent, int32_t* __restrict__ root_rank,
-    int32_t* __restrict__ labels_kept, int32_t* __restrict__ labels_full, int32_t* __restrict__ n_clusters) {
+// ---- labelling: (a) rank the roots in index order (one CTA per scan, ordered scan),
+//                 (b) cores take the rank of their root, (c) borders take the smallest cluster id
+//                 among their core neighbours; (b),(c) run grid-wide.
+__global__ void __launch_bounds__(1024) dbscan_rank_roots_kernel(
+    const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, const uint8_t* __restrict__ core,
+    const int32_t* __restrict__ parent, int32_t* __restrict__ root_rank, int32_t* __restrict__ n_clusters) {
   const int s = blockIdx.x;
   const int n = n_kept[s];
   const int64_t base = off[s];
-  const int n_full = (int)(off[s + 1] - base);
-  int32_t* par = parent + base;
   __shared__ int warp_cnt[32];
   __shared__ int tile_total;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < n_full; i += blockDim.x) labels_full[base + i] = -1;
-  // roots are exactly the core points that are their own parent; rank them in index order
   int running = 0;
   for (int t0 = 0; t0 < n; t0 += 1024) {
     const int i = t0 + threadIdx.x;
-    const bool is_root = i < n && core[base + i] && par[i] == i;
+    const bool is_root = i < n && core[base + i] && parent[base + i] == i;
     const unsigned bal = __ballot_sync(0xffffffffu, is_root);
     if (lane == 0) warp_cnt[w] = __popc(bal);
     __syncthreads();
@@ -411,34 +410,65 @@ __global__ void __launch_bounds__(1024) dbscan_label_kernel(
     __syncthreads();
   }
   if (threadIdx.x == 0) n_clusters[s] = running;
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    if (core[base + i]) {
-      int r = i;
-      while (par[r] != r) r = par[r];
-      labels_kept[base + i] = root_rank[base + r];
+}
+
+__global__ void __launch_bounds__(256) dbscan_label_cores_kernel(
+    const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, const uint8_t* __restrict__ core,
+    const int32_t* __restrict__ parent, const int32_t* __restrict__ root_rank, int32_t* __restrict__ labels_kept,
+    int32_t* __restrict__ labels_full) {
+  const int s = blockIdx.y;
+  const int n = n_kept[s];
+  const int64_t base = off[s];
+  const int n_full = (int)(off[s + 1] - base);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_full; i += gridDim.x * blockDim.x) {
+    labels_full[base + i] = -1;
+    if (i < n) {
+      int lab = -1;
+      if (core[base + i]) {
+        int r = i;
+        while (parent[base + r] != r) r = parent[base + r];
+        lab = root_rank[base + r];
+      }
+      labels_kept[base + i] = lab;
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+}
+
+__global__ void __launch_bounds__(256) dbscan_label_borders_kernel(
+    const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, const int32_t* __restrict__ kept_idx, int k_nn,
+    const int32_t* __restrict__ nbr, const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt, double eps,
+    const uint8_t* __restrict__ core, const int32_t* __restrict__ labels_kept, int32_t* __restrict__ border_lab,
+    int32_t* __restrict__ labels_full) {
+  const int s = blockIdx.y;
+  const int n = n_kept[s];
+  const int64_t base = off[s];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int lab;
     if (core[base + i]) {
       lab = labels_kept[base + i];
     } else {
       lab = 0x7fffffff;
       const int m = nbr_cnt[base + i];
+      const size_t row = (size_t)(base + i) * k_nn;
       for (int c = 0; c < m; ++c) {
-        const int j = nbr[(size_t)(base + i) * k_nn + c];
-        if (core[base + j] && (double)nbr_w[(size_t)(base + i) * k_nn + c] <= eps) lab = min(lab, labels_kept[base + j]);
+        const int j = nbr[row + c];
+        if (core[base + j] && (double)nbr_w[row + c] <= eps) lab = min(lab, labels_kept[base + j]);
       }
       if (lab == 0x7fffffff) lab = -1;
+      border_lab[base + i] = lab;       // labels_kept of cores is still being read by other threads
     }
     labels_full[base + kept_idx[base + i]] = lab;
-    if (!core[base + i]) root_rank[base + i] = lab;   // stash; copied back below
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    if (!core[base + i]) labels_kept[base + i] = root_rank[base + i];
+}
+
+__global__ void __launch_bounds__(256) dbscan_merge_borders_kernel(
+    const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, const uint8_t* __restrict__ core,
+    const int32_t* __restrict__ border_lab, int32_t* __restrict__ labels_kept) {
+  const int s = blockIdx.y;
+  const int n = n_kept[s];
+  const int64_t base = off[s];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (!core[base + i]) labels_kept[base + i] = border_lab[base + i];
 }
 
 }  // namespace modest
@@ -560,21 +590,29 @@ extern "C" int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept
   uint8_t* core = ar.take<uint8_t>(n_points_total);
   int32_t* parent = ar.take<int32_t>(n_points_total);
   int32_t* root_rank = ar.take<int32_t>(n_points_total);
+  int32_t* border_lab = root_rank;
   int pblocks = (int)((max_points + 255) / 256);
   if (pblocks < 1) pblocks = 1;
   dbscan_core_kernel<<<dim3(pblocks, n_scans), 256, 0, stream>>>(d_off, d_n_kept, n_neighbors, d_nbr_w, d_nbr_cnt,
                                                                 eps, min_samples, core, parent);
   MODEST_LAUNCH_CHECK("dbscan_core_kernel");
-  int64_t eb = (max_points * n_neighbors + 255) / 256;
+  int64_t eb = (max_points * 32 + 255) / 256;          // one warp per row
   if (eb < 1) eb = 1;
-  if (eb > 148 * 32) eb = 148 * 32;
+  if (eb > 148 * 16) eb = 148 * 16;
   dbscan_union_kernel<<<dim3((unsigned)eb, n_scans), 256, 0, stream>>>(d_off, d_n_kept, n_neighbors, d_nbr, d_nbr_w,
                                                                       d_nbr_cnt, eps, core, parent);
   MODEST_LAUNCH_CHECK("dbscan_union_kernel");
-  dbscan_label_kernel<<<n_scans, 1024, 0, stream>>>(d_off, d_n_kept, d_kept_idx, n_neighbors, d_nbr, d_nbr_w,
-                                                    d_nbr_cnt, eps, core, parent, root_rank, d_labels_kept,
-                                                    d_labels_full, d_n_clusters);
-  MODEST_LAUNCH_CHECK("dbscan_label_kernel");
-  note_launch(3);
+  dbscan_rank_roots_kernel<<<n_scans, 1024, 0, stream>>>(d_off, d_n_kept, core, parent, root_rank, d_n_clusters);
+  MODEST_LAUNCH_CHECK("dbscan_rank_roots_kernel");
+  const dim3 pgrid(pblocks, n_scans);
+  dbscan_label_cores_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_n_kept, core, parent, root_rank, d_labels_kept, d_labels_full);
+  MODEST_LAUNCH_CHECK("dbscan_label_cores_kernel");
+  // root_rank entries of non-root points are free: reuse the array for the border labels
+  dbscan_label_borders_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_n_kept, d_kept_idx, n_neighbors, d_nbr, d_nbr_w, d_nbr_cnt, eps,
+                                                        core, d_labels_kept, border_lab, d_labels_full);
+  MODEST_LAUNCH_CHECK("dbscan_label_borders_kernel");
+  dbscan_merge_borders_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_n_kept, core, border_lab, d_labels_kept);
+  MODEST_LAUNCH_CHECK("dbscan_merge_borders_kernel");
+  note_launch(6);
   return MODEST_OK;
 }
