@@ -153,7 +153,7 @@ def run_ours(args):
     ptc_host = [torch.from_numpy(c.query).pin_memory() for c in cases]
     calibs = [c.calib for c in cases]
     h2d_bytes = sum(t.numel() * 4 for t in q_fixed) + sum(t.numel() * 4 for h in hist for t in h) + \
-        sum(t.numel() * 4 for t in ptc_host)
+        sum(t.numel() * 4 for t in ptc_host)     # == host_batch.h2d_bytes
 
     scorer = pp_mod.PPScorer()
     pipe = pl.SeedLabelPipeline()
@@ -166,18 +166,22 @@ def run_ours(args):
         scorer(pp_batch, out=pp_out)
         return pipe.run(scan_batch, rng="device", seed=seed)
 
+    from modest_b200 import engine as eng
+    host_batch = eng.make_host_batch([c.query_fixed for c in cases], [c.history for c in cases],
+                                     [c.query for c in cases], calibs, scan_ids=[rank * B + s for s in range(B)])
+    engine = eng.SeedLabelEngine()
     d2h_bytes = [0]
 
-    def e2e_step(seed):
-        b = pp_mod.pack_batch(q_fixed, hist)                    # H2D of query + history
-        pp = scorer(b)
-        sb = pl.make_batch(ptc_host, [pp[b.h_q_off[s]:b.h_q_off[s + 1]] for s in range(B)], calibs)   # H2D of raw scans
-        res = pipe.run(sb, rng="device", seed=seed)
-        texts = pipe.label_texts(sb, res.boxes, res.n_boxes, res.keep)     # D2H + host text
-        d2h_bytes[0] = res.boxes.numel() * 8 + res.n_boxes.numel() * 4 + res.keep.numel()
-        if world > 1:
-            dist.gather_blobs({rank * B + s: t.encode() for s, t in enumerate(texts)})
-        return texts
+    def e2e_run(n_steps):
+        """The public streaming API: pinned host batches in, label text out; H2D of batch k+1
+        overlaps the kernels of batch k and the text formatting of batch k-1."""
+        n_lines = 0
+        for ids, texts in engine.process(host_batch for _ in range(n_steps)):
+            if world > 1:
+                dist.gather_blobs({i: t.encode() for i, t in zip(ids, texts)})
+            n_lines += sum(t.count("\n") + 1 for t in texts if t)
+        d2h_bytes[0] = engine.d2h_bytes_last
+        return n_lines
 
     def barrier():
         if world > 1:
@@ -210,12 +214,10 @@ def run_ours(args):
     n_boxes = int(res.n_boxes.sum().item())
 
     # ---- e2e (host buffers in, label text out)
-    for w in range(2):
-        e2e_step(w)
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        e2e_step(200 + k)
+    e2e_run(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
 

@@ -139,7 +139,91 @@ __device__ __forceinline__ void for_each_candidate(const float4* __restrict__ so
   }
 }
 
-__global__ void __launch_bounds__(128) knn_select_kernel(
+// Exact k-th smallest of the values a `scan` enumerates (those <= R2), by nested 256-bin
+// histograms over d2 followed by an exact ranking of the <= 32 members of the final bin.
+// `scan(f)` must call f(live, d2, j) convergently for every candidate slot; it may be replayed.
+// Returns false when fewer than k_nn values are <= R2 (then *rk2 is untouched).
+template <typename Scan>
+__device__ __forceinline__ bool kth_by_histogram(Scan scan, int k_nn, double R2, int* hist, int lane, double* rk2,
+                                                 int32_t* flags) {
+  BinChain ch;
+  ch.depth = 0;
+  ch.lo[0] = 0.0;
+  ch.scale[0] = (double)kBins / (R2 * (1.0 + 1e-12) + 1e-300);
+  int need = k_nn;
+  for (int round = 0; round < kMaxDepth; ++round) {
+    for (int b = lane; b < kBins; b += 32) hist[b] = 0;
+    __syncwarp();
+    scan([&](bool live, double d2, int) {
+      int b;
+      if (live && d2 <= R2 && chain_bin(ch, d2, &b)) atomicAdd(&hist[b], 1);
+    });
+    __syncwarp();
+    int loc[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { loc[j] = hist[lane * 8 + j]; tot += loc[j]; }
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    if (round == 0 && total < k_nn) return false;
+    int exc = inc - tot, selbin = -1, below = 0, inbin = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (selbin < 0 && exc + loc[j] >= need && need > exc) { selbin = lane * 8 + j; below = exc; inbin = loc[j]; }
+      exc += loc[j];
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, selbin >= 0);
+    const int src = __ffs(who) - 1;
+    selbin = __shfl_sync(0xffffffffu, selbin, src);
+    below = __shfl_sync(0xffffffffu, below, src);
+    inbin = __shfl_sync(0xffffffffu, inbin, src);
+    need -= below;
+    ch.sel[ch.depth] = selbin;
+    if (inbin <= 32 || round == kMaxDepth - 1) {
+      const int closed = ch.depth + 1;
+      double mine = __longlong_as_double(0x7ff0000000000000ll);
+      int have = 0;
+      scan([&](bool live, double d2, int) {
+        bool in = live && d2 <= R2;
+        if (in)
+          for (int l = 0; l < closed; ++l) in = in && (bin_of(d2, ch.lo[l], ch.scale[l]) == ch.sel[l]);
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const int slot = have + __popc(bal & ((1u << lane) - 1u));
+        for (unsigned rem = bal; rem; rem &= rem - 1) {
+          const int srcl = __ffs(rem) - 1;
+          const int dst = __shfl_sync(0xffffffffu, slot, srcl);
+          const double v = __shfl_sync(0xffffffffu, d2, srcl);
+          if (lane == dst) mine = v;
+        }
+        have += __popc(bal);
+      });
+      if (inbin > 32 && lane == 0) atomicOr(flags, 1);          // unresolved tie block
+      int rank = 0;
+      for (int l2 = 0; l2 < 32; ++l2) {
+        const double v = __shfl_sync(0xffffffffu, mine, l2);
+        rank += (v < mine) || (v == mine && l2 < lane);
+      }
+      const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < have);
+      const int srcl = hitl ? __ffs(hitl) - 1 : 0;
+      *rk2 = __shfl_sync(0xffffffffu, mine, srcl);
+      return true;
+    }
+    const double wbin = 1.0 / ch.scale[ch.depth];
+    ch.lo[ch.depth + 1] = ch.lo[ch.depth] + (double)selbin * wbin;
+    ch.scale[ch.depth + 1] = ch.scale[ch.depth] * (double)kBins;
+    ch.depth += 1;
+  }
+  return true;
+}
+
+constexpr int kKnnWarps = 4;
+constexpr int kListCap = 384;      // (d2, j) pairs cached per warp between the passes
+
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
     const float4* __restrict__ sorted_all, const int* __restrict__ cells_all, const GridMeta* __restrict__ meta,
     const int64_t* __restrict__ off, int G, int k_nn, double r2_max, int L_fine, double r2_fine, int L_coarse,
     double* __restrict__ rk2_all, int32_t* __restrict__ knn_all, int32_t* __restrict__ knn_cnt_all,
@@ -149,129 +233,98 @@ __global__ void __launch_bounds__(128) knn_select_kernel(
   const int n = m.n;
   const float4* __restrict__ sorted = sorted_all + off[s];
   const int* __restrict__ cells = cells_all + (size_t)s * cell_stride(G);
-  __shared__ int hist_sh[4][kBins];
+  __shared__ int hist_sh[kKnnWarps][kBins];
+  __shared__ double list_d2[kKnnWarps][kListCap];
+  __shared__ int list_j[kKnnWarps][kListCap];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   int* hist = hist_sh[wib];
-  const int warps_per_grid = gridDim.x * 4;
+  double* ld2 = list_d2[wib];
+  int* lj = list_j[wib];
+  const int warps_per_grid = gridDim.x * kKnnWarps;
 
-  for (int pos = blockIdx.x * 4 + wib; pos < n; pos += warps_per_grid) {
+  for (int pos = blockIdx.x * kKnnWarps + wib; pos < n; pos += warps_per_grid) {
     const float4 p = sorted[pos];
     const int i = __float_as_int(p.w);
     const int cx = cell_coord(p.x, m.x0, m.inv_cell), cy = cell_coord(p.y, m.y0, m.inv_cell);
     double rk2 = __longlong_as_double(0x7ff0000000000000ll);   // +inf
-    int L = L_fine;
-    double R2 = r2_fine;
-    bool bounded = false;          // true once we know >= k others lie within R2 at level L
-    for (int level = 0; level < 2 && !bounded; ++level) {
-      if (level == 1) { L = L_coarse; R2 = r2_max; }
-      // ---- round 0: histogram of d2 over [0, R2] ----
-      BinChain ch;
-      ch.depth = 0;
-      ch.lo[0] = 0.0;
-      ch.scale[0] = (double)kBins / (R2 * (1.0 + 1e-12) + 1e-300);
-      int need = k_nn;             // rank (1-based) of the wanted element among those in the open range
-      bool done = false;
-      for (int round = 0; round < kMaxDepth && !done; ++round) {
-        for (int b = lane; b < kBins; b += 32) hist[b] = 0;
-        __syncwarp();
-        for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
-          if (live) {
-            const double d2 = sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z);
-            int b;
-            if (d2 <= R2 && chain_bin(ch, d2, &b)) atomicAdd(&hist[b], 1);
-          }
-        });
-        __syncwarp();
-        // warp prefix over 256 bins: lane owns 8 consecutive bins
-        int loc[8], tot = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { loc[j] = hist[lane * 8 + j]; tot += loc[j]; }
-        int inc = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int u = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += u;
-        }
-        const int total = __shfl_sync(0xffffffffu, inc, 31);
-        if (round == 0 && total < k_nn) break;   // fewer than k others within R2 at this level
-        bounded = true;
-        // find the bin holding rank `need`
-        int exc = inc - tot, selbin = -1, below = 0, inbin = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (selbin < 0 && exc + loc[j] >= need && need > exc) { selbin = lane * 8 + j; below = exc; inbin = loc[j]; }
-          exc += loc[j];
-        }
-        const unsigned who = __ballot_sync(0xffffffffu, selbin >= 0);
-        const int src = __ffs(who) - 1;
-        selbin = __shfl_sync(0xffffffffu, selbin, src);
-        below = __shfl_sync(0xffffffffu, below, src);
-        inbin = __shfl_sync(0xffffffffu, inbin, src);
-        need -= below;
-        ch.sel[ch.depth] = selbin;
-        if (inbin <= 32 || round == kMaxDepth - 1) {
-          // ---- gather the <= 32 members of the selected bin, rank them exactly ----
-          const int closed = ch.depth + 1;
-          double mine = __longlong_as_double(0x7ff0000000000000ll);
-          int have = 0;
-          for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
-            bool in = false;
-            double d2 = 0.0;
-            if (live) {
-              d2 = sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z);
-              if (d2 <= R2) {
-                in = true;
-                for (int l = 0; l < closed; ++l) in = in && (bin_of(d2, ch.lo[l], ch.scale[l]) == ch.sel[l]);
-              }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, in);
-            const int slot = have + __popc(bal & ((1u << lane) - 1u));
-            // hand each member to the lane whose id equals its slot
-            for (unsigned rem = bal; rem; rem &= rem - 1) {
-              const int srcl = __ffs(rem) - 1;
-              const int dst = __shfl_sync(0xffffffffu, slot, srcl);
-              const double v = __shfl_sync(0xffffffffu, d2, srcl);
-              if (lane == dst) mine = v;
-            }
-            have += __popc(bal);
-          });
-          if (inbin > 32) { if (lane == 0) atomicOr(flags, 1); }   // unresolved tie block
-          // exact rank: number of members strictly smaller (ties broken by lane)
-          int rank = 0;
-          for (int l2 = 0; l2 < 32; ++l2) {
-            const double v = __shfl_sync(0xffffffffu, mine, l2);
-            rank += (v < mine) || (v == mine && l2 < lane);
-          }
-          const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < have);
-          const int srcl = hitl ? __ffs(hitl) - 1 : 0;
-          rk2 = __shfl_sync(0xffffffffu, mine, srcl);
-          done = true;
-        } else {
-          // descend: split the selected bin into 256 sub-bins
-          const double w = 1.0 / ch.scale[ch.depth];
-          ch.lo[ch.depth + 1] = ch.lo[ch.depth] + (double)selbin * w;
-          ch.scale[ch.depth + 1] = ch.scale[ch.depth] * (double)kBins;
-          ch.depth += 1;
-        }
-      }
-    }
-    // ---- emit { j : d2 <= min(rk2, r2_max) } using the level that decided rk2 -------------
-    const double cut = fmin(rk2, r2_max);
     int32_t* out = knn_all + ((size_t)off[s] + i) * k_nn;
-    int have = 0;
-    for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
-      bool in = false;
-      if (live) in = sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z) <= cut;
-      const unsigned bal = __ballot_sync(0xffffffffu, in);
-      const int slot = have + __popc(bal & ((1u << lane) - 1u));
-      if (in && slot < k_nn) out[slot] = __float_as_int(q.w);
-      have += __popc(bal);
-    });
-    if (lane == 0) {
-      if (have > k_nn) { atomicOr(flags, 2); have = k_nn; }   // ties beyond k: list truncated
-      rk2_all[off[s] + i] = rk2;
-      knn_cnt_all[off[s] + i] = have;
+    int emitted = 0;
+    bool done = false;
+    for (int level = 0; level < 2 && !done; ++level) {
+      const int L = level == 0 ? L_fine : L_coarse;
+      const double R2 = level == 0 ? r2_fine : r2_max;
+      // ---- pass A: one sweep of the window, caching every candidate within R2 ----
+      int cnt = 0;
+      for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
+        double d2 = 0.0;
+        bool in = false;
+        if (live) { d2 = sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z); in = d2 <= R2; }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
+        if (in && slot < kListCap) { ld2[slot] = d2; lj[slot] = __float_as_int(q.w); }
+        cnt += __popc(bal);
+      });
+      __syncwarp();
+      if (level == 0 && cnt < k_nn) continue;                    // not enough within the fine window
+      if (cnt < k_nn) {                                          // fewer than k within the radius: all of them
+        if (cnt <= kListCap) {
+          for (int e = lane; e < cnt; e += 32) out[e] = lj[e];
+          emitted = cnt;
+        } else {
+          for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
+            const bool in = live && sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z) <= R2;
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            const int slot = emitted + __popc(bal & ((1u << lane) - 1u));
+            if (in && slot < k_nn) out[slot] = __float_as_int(q.w);
+            emitted += __popc(bal);
+          });
+        }
+        done = true;
+        break;
+      }
+      if (cnt <= kListCap) {
+        // ---- selection and emission entirely from the cached list ----
+        auto scan_list = [&](auto f) {
+          for (int e0 = 0; e0 < cnt; e0 += 32) {
+            const int e = e0 + lane;
+            const bool live = e < cnt;
+            f(live, live ? ld2[e] : 0.0, live ? lj[e] : 0);
+          }
+        };
+        kth_by_histogram(scan_list, k_nn, R2, hist, lane, &rk2, flags);
+        const double cut = fmin(rk2, r2_max);
+        scan_list([&](bool live, double d2, int j) {
+          const bool in = live && d2 <= cut;
+          const unsigned bal = __ballot_sync(0xffffffffu, in);
+          const int slot = emitted + __popc(bal & ((1u << lane) - 1u));
+          if (in && slot < k_nn) out[slot] = j;
+          emitted += __popc(bal);
+        });
+      } else {
+        // ---- list overflow (very dense neighbourhood): replay the window for every pass ----
+        auto scan_grid = [&](auto f) {
+          for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
+            f(live, live ? sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z) : 0.0, __float_as_int(q.w));
+          });
+        };
+        kth_by_histogram(scan_grid, k_nn, R2, hist, lane, &rk2, flags);
+        const double cut = fmin(rk2, r2_max);
+        scan_grid([&](bool live, double d2, int j) {
+          const bool in = live && d2 <= cut;
+          const unsigned bal = __ballot_sync(0xffffffffu, in);
+          const int slot = emitted + __popc(bal & ((1u << lane) - 1u));
+          if (in && slot < k_nn) out[slot] = j;
+          emitted += __popc(bal);
+        });
+      }
+      done = true;
     }
+    if (lane == 0) {
+      if (emitted > k_nn) { atomicOr(flags, 2); emitted = k_nn; }   // ties beyond k: list truncated
+      rk2_all[off[s] + i] = rk2;
+      knn_cnt_all[off[s] + i] = emitted;
+    }
+    __syncwarp();
   }
 }
 
@@ -557,7 +610,7 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
   if (wblocks < 1) wblocks = 1;
   if (wblocks > 148 * 16) wblocks = 148 * 16;
   MODEST_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t), stream));
-  knn_select_kernel<<<dim3(wblocks, n_scans), 128, 0, stream>>>(sorted, cells, meta, d_off, G, n_neighbors, r2_max,
+  knn_select_kernel<<<dim3(wblocks, n_scans), kKnnWarps * 32, 0, stream>>>(sorted, cells, meta, d_off, G, n_neighbors, r2_max,
                                                                L_fine, r2_fine, L_coarse, rk2, knn, knn_cnt, d_flags);
   MODEST_LAUNCH_CHECK("knn_select_kernel");
   int mblocks = (int)((max_points * 32 + 255) / 256);

@@ -1,0 +1,182 @@
+"""Streaming front end of the seed-label path: host batches in, KITTI label text out.
+
+`SeedLabelEngine.process(host_batches)` is the call a user of the fused path makes (the CLIs use
+the same stages one scan at a time for RNG parity).  It overlaps the three phases of consecutive
+batches on two CUDA streams:
+
+    copy stream    : pinned host -> device copies of batch k+1
+    compute stream : PP score + seed-label pipeline of batch k
+    host           : device -> host copy of the (small) box tables of batch k-1 and label text
+
+Inputs per scan are what the reference's programs hold in memory just before their numeric
+stages: the query scan in the fixed frame and the per-traversal history clouds
+(pre_compute_pp_score.py:188), the raw scan (generate_mask.py:52) and its calibration.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import pipeline as pl
+from . import pp_score as pp_mod
+
+
+@dataclass
+class HostBatch:
+    """One batch in pinned host memory, scans concatenated."""
+    query_xyz: torch.Tensor      # (NQ,3) f32 pinned, fixed frame
+    hist_xyz: torch.Tensor       # (NH,3) f32 pinned, fixed frame, traversals concatenated
+    ptc: torch.Tensor            # (NQ,4) f32 pinned, raw scans
+    q_sizes: list                # points per scan
+    trav_sizes: list             # list (per scan) of lists (per traversal) of point counts
+    calibs: list                 # per scan dict / Calibration
+    scan_ids: list = field(default_factory=list)
+
+    @property
+    def h2d_bytes(self):
+        return 4 * (self.query_xyz.numel() + self.hist_xyz.numel() + self.ptc.numel())
+
+
+def make_host_batch(queries_fixed, histories, ptcs, calibs, scan_ids=None) -> HostBatch:
+    """Pack per-scan numpy arrays into one pinned staging buffer per array kind (what a loader
+    that reads .bin files straight into pinned memory would produce)."""
+    def pin(arrs, width):
+        n = sum(int(a.shape[0]) for a in arrs)
+        t = torch.empty((n, width), dtype=torch.float32).pin_memory()
+        o = 0
+        for a in arrs:
+            a = np.asarray(a, dtype=np.float32)[:, :width]
+            t[o:o + len(a)] = torch.from_numpy(np.ascontiguousarray(a))
+            o += len(a)
+        return t
+    flat_hist = [t for h in histories for t in h]
+    return HostBatch(query_xyz=pin(queries_fixed, 3), hist_xyz=pin(flat_hist, 3), ptc=pin(ptcs, 4),
+                     q_sizes=[int(q.shape[0]) for q in queries_fixed],
+                     trav_sizes=[[int(t.shape[0]) for t in h] for h in histories], calibs=list(calibs),
+                     scan_ids=list(scan_ids) if scan_ids is not None else list(range(len(ptcs))))
+
+
+class _Slot:
+    """Device-side staging for one in-flight batch."""
+
+    def __init__(self):
+        self.bufs = {}
+        self.ready = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+        self.pp_batch = None
+        self.scan_batch = None
+        self.result = None
+        self.host = None
+
+    def pinned(self, name, shape, dtype):
+        t = self.bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+            self.bufs[name] = t
+        return t
+
+    def buf(self, name, shape, dtype):
+        n = int(np.prod(shape))
+        t = self.bufs.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device="cuda")
+            self.bufs[name] = t
+        return t[:n].view(*shape)
+
+
+class SeedLabelEngine:
+    def __init__(self, cfg=None, radius=0.3, grid_dim=512, max_clusters=2048, max_boxes=128, seed=0):
+        self.pipe = pl.SeedLabelPipeline(cfg, max_clusters=max_clusters, max_boxes=max_boxes)
+        self.scorer = pp_mod.PPScorer(radius=radius, grid_dim=grid_dim)
+        self.copy_stream = torch.cuda.Stream()
+        self.compute_stream = torch.cuda.Stream()
+        self.slots = [_Slot(), _Slot()]
+        self.seed = int(seed)
+        self.d2h_bytes_last = 0
+
+    # ---- stage 1: host -> device on the copy stream ------------------------------------------
+    def _upload(self, slot: _Slot, hb: HostBatch):
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot.done)                # buffers free again?
+            q = slot.buf("q", hb.query_xyz.shape, torch.float32)
+            h = slot.buf("h", hb.hist_xyz.shape, torch.float32)
+            p = slot.buf("p", hb.ptc.shape, torch.float32)
+            q.copy_(hb.query_xyz, non_blocking=True)
+            h.copy_(hb.hist_xyz, non_blocking=True)
+            p.copy_(hb.ptc, non_blocking=True)
+            q_sizes = hb.q_sizes
+            trav_counts = [len(t) for t in hb.trav_sizes]
+            h_sizes = [m for t in hb.trav_sizes for m in t]
+            q_off = np.concatenate([[0], np.cumsum(q_sizes)]).astype(np.int64)
+            h_off = np.concatenate([[0], np.cumsum(h_sizes)]).astype(np.int64)
+            trav_off = np.concatenate([[0], np.cumsum(trav_counts)]).astype(np.int32)
+            count_off = np.concatenate([[0], np.cumsum(np.array(q_sizes, np.int64) * np.array(trav_counts, np.int64))]).astype(np.int64)
+            small = np.concatenate([q_off, h_off, count_off]).astype(np.int64)
+            small_d = slot.buf("off", small.shape, torch.int64)
+            small_d.copy_(torch.from_numpy(small), non_blocking=False)
+            trav_d = slot.buf("trav", trav_off.shape, torch.int32)
+            trav_d.copy_(torch.from_numpy(trav_off), non_blocking=False)
+            a, b = len(q_off), len(q_off) + len(h_off)
+            crow = np.stack([pl.calib_row(c) for c in hb.calibs])
+            calib_d = slot.buf("calib", crow.shape, torch.float64)
+            calib_d.copy_(torch.from_numpy(crow), non_blocking=False)
+            slot.pp_batch = pp_mod.PPBatch(
+                q, small_d[:a], h, small_d[a:b], trav_d, small_d[b:], n_scans=len(q_sizes), n_trav_total=int(trav_off[-1]),
+                n_query_total=int(q_off[-1]), n_count_total=int(count_off[-1]), max_query_points=max(q_sizes),
+                max_trav_points=max(h_sizes), h_q_off=q_off, h_trav_off=trav_off, h_count_off=count_off)
+            pp = slot.buf("pp", (int(q_off[-1]),), torch.float32)
+            slot.scan_batch = pl.ScanBatch(ptc=p, off=small_d[:a], pp=pp, calib=calib_d,
+                                           P2=np.stack([pl.calib_P2(c) for c in hb.calibs]), h_off=q_off,
+                                           scan_ids=hb.scan_ids)
+            slot.host = hb
+            slot.ready.record(self.copy_stream)
+
+    # ---- stage 2: kernels on the compute stream ---------------------------------------------------
+    def _compute(self, slot: _Slot, step: int):
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(slot.ready)
+            self.scorer(slot.pp_batch, out=slot.scan_batch.pp, stream=self.compute_stream)
+            slot.result = self.pipe.run(slot.scan_batch, rng="device", seed=self.seed + step, stream=self.compute_stream)
+            r = slot.result
+            # small results to pinned host memory, still on the compute stream
+            r.h_boxes = slot.pinned("h_boxes", r.boxes.shape, torch.float64)
+            r.h_n = slot.pinned("h_n", r.n_boxes.shape, torch.int32)
+            r.h_keep = slot.pinned("h_keep", r.keep.shape, torch.uint8)
+            r.h_boxes.copy_(r.boxes, non_blocking=True)
+            r.h_n.copy_(r.n_boxes, non_blocking=True)
+            r.h_keep.copy_(r.keep, non_blocking=True)
+            slot.done.record(self.compute_stream)
+
+    # ---- stage 3: label text on the host ----------------------------------------------------------
+    def _finish(self, slot: _Slot):
+        slot.done.synchronize()
+        r, b = slot.result, slot.scan_batch
+        hb_, hn, hk = r.h_boxes.numpy(), r.h_n.numpy(), r.h_keep.numpy()
+        self.d2h_bytes_last = hb_.nbytes + hn.nbytes + hk.nbytes
+        return [self.pipe.format_labels(hb_[s, :hn[s]], hk[s, :hn[s]], b.P2[s])[0] for s in range(b.n_scans)]
+
+    def process(self, host_batches):
+        """Generator: yields (scan_ids, [label text per scan]) for every batch, in order."""
+        pending = None
+        step = 0
+        it = iter(host_batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        self._upload(self.slots[0], nxt)
+        while nxt is not None:
+            cur_slot = self.slots[step % 2]
+            cur = nxt
+            nxt = next(it, None)
+            self._compute(cur_slot, step)
+            if nxt is not None:
+                self._upload(self.slots[(step + 1) % 2], nxt)
+            if pending is not None:
+                yield pending.host.scan_ids, self._finish(pending)
+            pending = cur_slot
+            step += 1
+            del cur
+        if pending is not None:
+            yield pending.host.scan_ids, self._finish(pending)
