@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) pp_scatter_kernel(const float* __restrict
 // concatenated candidate sequence, whichever point it belongs to -- so the SIMT lanes stay busy.
 constexpr int kCountWarps = 8;
 
-__global__ void __launch_bounds__(kCountWarps * 32) pp_count_kernel(
+__global__ void __launch_bounds__(kCountWarps * 32, 6) pp_count_kernel(
     const float* __restrict__ h_xyz, const int64_t* __restrict__ h_off, const int32_t* __restrict__ trav_scan,
     const int32_t* __restrict__ trav_off, const int64_t* __restrict__ q_off, const int64_t* __restrict__ count_off,
     const PPMeta* __restrict__ meta, const int2* __restrict__ cols, const int* __restrict__ zc,
@@ -321,26 +321,35 @@ __global__ void __launch_bounds__(kCountWarps * 32) pp_count_kernel(
       const int za = clampi(cz - 1, 0, kZCells - 1), zb = clampi(cz + 1, 0, kZCells - 1);
       const unsigned below_a = below_mask(za), upto_b = below_mask(zb + 1);
       const unsigned want = upto_b & ~below_a;
+      // staged so that the 9 record loads, then the (up to 18) cell-start loads, are each in
+      // flight together instead of one dependent round trip per column
+      int2 rec[9];
+      bool ok[9];
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        const int y = ya + dy;
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int x = xa + dx;
-          if (y <= yb && x <= xb) {
-            const int2 rec = __ldg(c + y * G + x);
-            const unsigned msk = (unsigned)rec.y;
-            if (msk & want) {
-              const int kb = __ldg(z + rec.x + __popc(msk & below_a));
-              const int ke = __ldg(z + rec.x + __popc(msk & upto_b));
-              rb[lane * 9 + nr] = kb;
-              re[lane * 9 + nr] = ke;
-              total += ke - kb;
-              ++nr;
-            }
-          }
-        }
+      for (int j = 0; j < 9; ++j) {
+        const int y = ya + j / 3, x = xa + j % 3;
+        ok[j] = (y <= yb) && (x <= xb);
+        rec[j] = ok[j] ? __ldg(c + y * G + x) : make_int2(0, 0);
       }
+      int kb[9], ke[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const unsigned msk = (unsigned)rec[j].y;
+        ok[j] = ok[j] && (msk & want);
+        kb[j] = rec[j].x + __popc(msk & below_a);      // compact-cell indices for now
+        ke[j] = rec[j].x + __popc(msk & upto_b);
+      }
+#pragma unroll
+      for (int j = 0; j < 9; ++j)
+        if (ok[j]) { kb[j] = __ldg(z + kb[j]); ke[j] = __ldg(z + ke[j]); }
+#pragma unroll
+      for (int j = 0; j < 9; ++j)
+        if (ok[j]) {
+          rb[lane * 9 + j] = kb[j];
+          re[lane * 9 + j] = ke[j];
+          total += ke[j] - kb[j];
+          nr |= 1 << j;                                  // nr is the 9-bit mask of live ranges
+        }
     }
     s_nr[w][lane] = nr;
     s_pt[w][0][lane] = hx; s_pt[w][1][lane] = hy; s_pt[w][2][lane] = hz;
@@ -368,12 +377,14 @@ __global__ void __launch_bounds__(kCountWarps * 32) pp_count_kernel(
     int off = my_begin - __shfl_sync(0xffffffffu, excl, src);
     int left = my_end - my_begin;
     if (left > 0) {
-      int j = 0;
-      int k = rb[src * 9], ke = re[src * 9];
-      while (off >= ke - k) {                                     // skip whole ranges (and empty lanes)
+      unsigned live = (unsigned)s_nr[w][src];                     // ranges of `src` not yet consumed
+      int j = __ffs(live) - 1;
+      live &= live - 1;
+      int k = rb[src * 9 + j], ke = re[src * 9 + j];
+      while (off >= ke - k) {                                     // skip whole ranges of this point
         off -= ke - k;
-        ++j;
-        while (j >= s_nr[w][src]) { ++src; j = 0; }
+        j = __ffs(live) - 1;
+        live &= live - 1;
         k = rb[src * 9 + j]; ke = re[src * 9 + j];
       }
       k += off;
@@ -387,12 +398,12 @@ __global__ void __launch_bounds__(kCountWarps * 32) pp_count_kernel(
         if (hit) atomicAdd(cnt + k, 1);
         if (--left == 0) break;
         if (++k >= ke) {
-          ++j;
-          if (j >= s_nr[w][src]) {
-            do { ++src; } while (s_nr[w][src] == 0);
-            j = 0;
+          if (live == 0) {                                        // next point that has candidates
+            do { ++src; live = (unsigned)s_nr[w][src]; } while (live == 0);
             px = s_pt[w][0][src]; py = s_pt[w][1][src]; pz = s_pt[w][2][src];
           }
+          j = __ffs(live) - 1;
+          live &= live - 1;
           k = rb[src * 9 + j]; ke = re[src * 9 + j];
         }
       }
