@@ -101,20 +101,23 @@ __global__ void __launch_bounds__(1024) ground_mask_compact_kernel(
 constexpr int kBins = 256;
 constexpr int kMaxDepth = 6;
 
+template <typename T>
 struct BinChain {            // nested linear binning of d2: level l keeps bin sel[l] of [lo[l], lo[l]+256/scale[l])
-  double lo[kMaxDepth], scale[kMaxDepth];
+  T lo[kMaxDepth], scale[kMaxDepth];
   int sel[kMaxDepth];
   int depth;
 };
 
-__device__ __forceinline__ int bin_of(double d2, double lo, double scale) {
-  const double t = (d2 - lo) * scale;
+template <typename T>
+__device__ __forceinline__ int bin_of(T d2, T lo, T scale) {
+  const T t = (d2 - lo) * scale;
   int b = (int)t;
   return b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
 }
 
 // true iff d2 passes every closed level of the chain; *last = bin at the open level `depth`
-__device__ __forceinline__ bool chain_bin(const BinChain& c, double d2, int* last) {
+template <typename T>
+__device__ __forceinline__ bool chain_bin(const BinChain<T>& c, T d2, int* last) {
   for (int l = 0; l < c.depth; ++l)
     if (bin_of(d2, c.lo[l], c.scale[l]) != c.sel[l]) return false;
   *last = bin_of(d2, c.lo[c.depth], c.scale[c.depth]);
@@ -134,7 +137,7 @@ __device__ __forceinline__ void for_each_candidate(const float4* __restrict__ so
       const bool live = k < ke && k != self_pos;
       float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
       if (live) q = __ldg(sorted + k);
-      f(live, q);            // called convergently by the whole warp
+      f(live, q, k);         // called convergently by the whole warp
     }
   }
 }
@@ -143,18 +146,18 @@ __device__ __forceinline__ void for_each_candidate(const float4* __restrict__ so
 // histograms over d2 followed by an exact ranking of the <= 32 members of the final bin.
 // `scan(f)` must call f(live, d2, j) convergently for every candidate slot; it may be replayed.
 // Returns false when fewer than k_nn values are <= R2 (then *rk2 is untouched).
-template <typename Scan>
-__device__ __forceinline__ bool kth_by_histogram(Scan scan, int k_nn, double R2, int* hist, int lane, double* rk2,
+template <typename T, typename Scan>
+__device__ __forceinline__ bool kth_by_histogram(Scan scan, int k_nn, T R2, int* hist, int lane, T* rk2,
                                                  int32_t* flags) {
-  BinChain ch;
+  BinChain<T> ch;
   ch.depth = 0;
-  ch.lo[0] = 0.0;
-  ch.scale[0] = (double)kBins / (R2 * (1.0 + 1e-12) + 1e-300);
+  ch.lo[0] = (T)0;
+  ch.scale[0] = (T)kBins / (R2 * (T)(1.0 + 1e-6) + (T)1e-30);
   int need = k_nn;
   for (int round = 0; round < kMaxDepth; ++round) {
     for (int b = lane; b < kBins; b += 32) hist[b] = 0;
     __syncwarp();
-    scan([&](bool live, double d2, int) {
+    scan([&](bool live, T d2, int) {
       int b;
       if (live && d2 <= R2 && chain_bin(ch, d2, &b)) atomicAdd(&hist[b], 1);
     });
@@ -185,9 +188,9 @@ __device__ __forceinline__ bool kth_by_histogram(Scan scan, int k_nn, double R2,
     ch.sel[ch.depth] = selbin;
     if (inbin <= 32 || round == kMaxDepth - 1) {
       const int closed = ch.depth + 1;
-      double mine = __longlong_as_double(0x7ff0000000000000ll);
+      T mine = (T)__longlong_as_double(0x7ff0000000000000ll);
       int have = 0;
-      scan([&](bool live, double d2, int) {
+      scan([&](bool live, T d2, int) {
         bool in = live && d2 <= R2;
         if (in)
           for (int l = 0; l < closed; ++l) in = in && (bin_of(d2, ch.lo[l], ch.scale[l]) == ch.sel[l]);
@@ -196,7 +199,7 @@ __device__ __forceinline__ bool kth_by_histogram(Scan scan, int k_nn, double R2,
         for (unsigned rem = bal; rem; rem &= rem - 1) {
           const int srcl = __ffs(rem) - 1;
           const int dst = __shfl_sync(0xffffffffu, slot, srcl);
-          const double v = __shfl_sync(0xffffffffu, d2, srcl);
+          const T v = __shfl_sync(0xffffffffu, d2, srcl);
           if (lane == dst) mine = v;
         }
         have += __popc(bal);
@@ -204,7 +207,7 @@ __device__ __forceinline__ bool kth_by_histogram(Scan scan, int k_nn, double R2,
       if (inbin > 32 && lane == 0) atomicOr(flags, 1);          // unresolved tie block
       int rank = 0;
       for (int l2 = 0; l2 < 32; ++l2) {
-        const double v = __shfl_sync(0xffffffffu, mine, l2);
+        const T v = __shfl_sync(0xffffffffu, mine, l2);
         rank += (v < mine) || (v == mine && l2 < lane);
       }
       const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < have);
@@ -212,17 +215,24 @@ __device__ __forceinline__ bool kth_by_histogram(Scan scan, int k_nn, double R2,
       *rk2 = __shfl_sync(0xffffffffu, mine, srcl);
       return true;
     }
-    const double wbin = 1.0 / ch.scale[ch.depth];
-    ch.lo[ch.depth + 1] = ch.lo[ch.depth] + (double)selbin * wbin;
-    ch.scale[ch.depth + 1] = ch.scale[ch.depth] * (double)kBins;
+    const T wbin = (T)1 / ch.scale[ch.depth];
+    ch.lo[ch.depth + 1] = ch.lo[ch.depth] + (T)selbin * wbin;
+    ch.scale[ch.depth + 1] = ch.scale[ch.depth] * (T)kBins;
     ch.depth += 1;
   }
   return true;
 }
 
 constexpr int kKnnWarps = 4;
-constexpr int kListCap = 384;      // (d2, j) pairs cached per warp between the passes
+constexpr int kListCap = 640;      // (f32 d2, sorted position) pairs cached per warp between the passes
 
+// One warp per point.  Pass A sweeps the cell window once, evaluating d2 in float32 and caching
+// (d2, position) of everything inside the window radius in shared memory.  The k-th smallest
+// f32 value v is then found on the cached list; because the f32 evaluation error eps is known,
+// the exact (f64) k-th value lies among the few entries within a band of v, every entry
+// clearly below the band is a neighbour, every entry clearly above is not, and only the band
+// entries are re-evaluated in sequential f64 (sklearn's arithmetic).  rk2 and the neighbour
+// sets are therefore exactly those of the all-f64 algorithm (kept as the overflow fallback).
 __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
     const float4* __restrict__ sorted_all, const int* __restrict__ cells_all, const GridMeta* __restrict__ meta,
     const int64_t* __restrict__ off, int G, int k_nn, double r2_max, int L_fine, double r2_fine, int L_coarse,
@@ -234,80 +244,66 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
   const float4* __restrict__ sorted = sorted_all + off[s];
   const int* __restrict__ cells = cells_all + (size_t)s * cell_stride(G);
   __shared__ int hist_sh[kKnnWarps][kBins];
-  __shared__ double list_d2[kKnnWarps][kListCap];
-  __shared__ int list_j[kKnnWarps][kListCap];
+  __shared__ float list_d2[kKnnWarps][kListCap];
+  __shared__ int list_pos[kKnnWarps][kListCap];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   int* hist = hist_sh[wib];
-  double* ld2 = list_d2[wib];
-  int* lj = list_j[wib];
+  float* ld2 = list_d2[wib];
+  int* lpos = list_pos[wib];
   const int warps_per_grid = gridDim.x * kKnnWarps;
+  const double kInf = __longlong_as_double(0x7ff0000000000000ll);
 
   for (int pos = blockIdx.x * kKnnWarps + wib; pos < n; pos += warps_per_grid) {
     const float4 p = sorted[pos];
     const int i = __float_as_int(p.w);
     const int cx = cell_coord(p.x, m.x0, m.inv_cell), cy = cell_coord(p.y, m.y0, m.inv_cell);
-    double rk2 = __longlong_as_double(0x7ff0000000000000ll);   // +inf
+    double rk2 = kInf;
     int32_t* out = knn_all + ((size_t)off[s] + i) * k_nn;
     int emitted = 0;
-    bool done = false;
-    for (int level = 0; level < 2 && !done; ++level) {
+    auto exact_d2 = [&](int kpos) {
+      const float4 q = __ldg(sorted + kpos);
+      return sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z);
+    };
+    for (int level = 0; level < 2; ++level) {
       const int L = level == 0 ? L_fine : L_coarse;
       const double R2 = level == 0 ? r2_fine : r2_max;
-      // ---- pass A: one sweep of the window, caching every candidate within R2 ----
+      if (level == 0) {        // cheap reject: fewer than k+1 points in the whole fine window
+        const int xa = clampi(cx - L, 0, G - 1), xb = clampi(cx + L, 0, G - 1);
+        const int ya = clampi(cy - L, 0, G - 1), yb = clampi(cy + L, 0, G - 1);
+        int tot = 0;
+        for (int y = ya; y <= yb; ++y) tot += __ldg(cells + y * G + xb + 1) - __ldg(cells + y * G + xa);
+        if (tot <= k_nn) continue;
+      }
+      // f32 evaluation error of d2 (coordinates up to ~1e2 m, d2 <= R2): a few ulps of d2 plus
+      // the rounding of the coordinate differences; eps is a safe absolute bound
+      const float eps = 4e-6f * (float)R2 + 1e-9f;
+      const float band = 8.0f * eps;
+      const float R2f_list = (float)R2 + band;          // cache everything that could be within R2
+      // ---- pass A ----
       int cnt = 0;
-      for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
-        double d2 = 0.0;
+      for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q, int kpos) {
+        float d2 = 0.f;
         bool in = false;
-        if (live) { d2 = sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z); in = d2 <= R2; }
+        if (live) {
+          const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+          d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          in = d2 <= R2f_list;
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, in);
         const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
-        if (in && slot < kListCap) { ld2[slot] = d2; lj[slot] = __float_as_int(q.w); }
+        if (in && slot < kListCap) { ld2[slot] = d2; lpos[slot] = kpos; }
         cnt += __popc(bal);
       });
       __syncwarp();
-      if (level == 0 && cnt < k_nn) continue;                    // not enough within the fine window
-      if (cnt < k_nn) {                                          // fewer than k within the radius: all of them
-        if (cnt <= kListCap) {
-          for (int e = lane; e < cnt; e += 32) out[e] = lj[e];
-          emitted = cnt;
-        } else {
-          for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
-            const bool in = live && sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z) <= R2;
-            const unsigned bal = __ballot_sync(0xffffffffu, in);
-            const int slot = emitted + __popc(bal & ((1u << lane) - 1u));
-            if (in && slot < k_nn) out[slot] = __float_as_int(q.w);
-            emitted += __popc(bal);
-          });
-        }
-        done = true;
-        break;
-      }
-      if (cnt <= kListCap) {
-        // ---- selection and emission entirely from the cached list ----
-        auto scan_list = [&](auto f) {
-          for (int e0 = 0; e0 < cnt; e0 += 32) {
-            const int e = e0 + lane;
-            const bool live = e < cnt;
-            f(live, live ? ld2[e] : 0.0, live ? lj[e] : 0);
-          }
-        };
-        kth_by_histogram(scan_list, k_nn, R2, hist, lane, &rk2, flags);
-        const double cut = fmin(rk2, r2_max);
-        scan_list([&](bool live, double d2, int j) {
-          const bool in = live && d2 <= cut;
-          const unsigned bal = __ballot_sync(0xffffffffu, in);
-          const int slot = emitted + __popc(bal & ((1u << lane) - 1u));
-          if (in && slot < k_nn) out[slot] = j;
-          emitted += __popc(bal);
-        });
-      } else {
-        // ---- list overflow (very dense neighbourhood): replay the window for every pass ----
+      if (cnt > kListCap) {
+        // ---- overflow (very dense neighbourhood): all-f64 algorithm, window replayed per pass ----
         auto scan_grid = [&](auto f) {
-          for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q) {
+          for_each_candidate(sorted, cells, G, cx, cy, L, pos, [&](bool live, const float4& q, int) {
             f(live, live ? sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z) : 0.0, __float_as_int(q.w));
           });
         };
-        kth_by_histogram(scan_grid, k_nn, R2, hist, lane, &rk2, flags);
+        const bool found = kth_by_histogram<double>(scan_grid, k_nn, R2, hist, lane, &rk2, flags);
+        if (!found && level == 0) continue;
         const double cut = fmin(rk2, r2_max);
         scan_grid([&](bool live, double d2, int j) {
           const bool in = live && d2 <= cut;
@@ -316,8 +312,74 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
           if (in && slot < k_nn) out[slot] = j;
           emitted += __popc(bal);
         });
+        break;
       }
-      done = true;
+      auto scan_list = [&](auto f) {
+        for (int e0 = 0; e0 < cnt; e0 += 32) {
+          const int e = e0 + lane;
+          const bool live = e < cnt;
+          f(live, live ? ld2[e] : 0.f, live ? lpos[e] : 0);
+        }
+      };
+      // number of entries certainly / possibly within R2 (exactly)
+      int sure = 0;
+      scan_list([&](bool live, float d2, int) {
+        sure += __popc(__ballot_sync(0xffffffffu, live && d2 < (float)R2 - band));
+      });
+      double cut = r2_max;              // exact cut-off for emission
+      float v32 = 0.f;
+      // fine level: only when k points are certainly inside the fine radius (the window then
+      // provably holds the k nearest); radius level: whenever k candidates are cached
+      if (sure >= k_nn || (level == 1 && cnt >= k_nn)) {
+        // find the k-th smallest on the f32 keys, then exactly inside the band around it
+        float v = 0.f;
+        kth_by_histogram<float>(scan_list, k_nn, R2f_list, hist, lane, &v, flags);
+        v32 = v;
+        int n_low = 0, n_band = 0;
+        double mine = kInf;
+        scan_list([&](bool live, float d2, int kpos) {
+          const bool low = live && d2 < v32 - band;
+          const bool inb = live && !low && d2 <= v32 + band;
+          n_low += __popc(__ballot_sync(0xffffffffu, low));
+          const unsigned bal = __ballot_sync(0xffffffffu, inb);
+          const int slot = n_band + __popc(bal & ((1u << lane) - 1u));
+          const double ex = inb ? exact_d2(kpos) : 0.0;
+          for (unsigned rem = bal; rem; rem &= rem - 1) {
+            const int srcl = __ffs(rem) - 1;
+            const int dst = __shfl_sync(0xffffffffu, slot, srcl);
+            const double vv = __shfl_sync(0xffffffffu, ex, srcl);
+            if (lane == dst) mine = vv;
+          }
+          n_band += __popc(bal);
+        });
+        if (n_band > 32) { if (lane == 0) atomicOr(flags, 1); }
+        const int need = k_nn - n_low;                     // 1-based rank inside the band
+        int rank = 0;
+        for (int l2 = 0; l2 < 32; ++l2) {
+          const double vv = __shfl_sync(0xffffffffu, mine, l2);
+          rank += (vv < mine) || (vv == mine && l2 < lane);
+        }
+        const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < min(n_band, 32));
+        if (hitl) rk2 = __shfl_sync(0xffffffffu, mine, __ffs(hitl) - 1);
+        else if (lane == 0) atomicOr(flags, 1);
+        cut = fmin(rk2, r2_max);
+      } else if (level == 0) {
+        continue;      // (also the borderline case: the radius level, whose window contains this one, decides)
+      }
+      // ---- emission from the list: sure-below, sure-above, or exact inside the band around cut ----
+      const float cutf = (float)cut;
+      scan_list([&](bool live, float d2, int kpos) {
+        bool in = false;
+        if (live) {
+          if (d2 < cutf - band) in = true;
+          else if (d2 <= cutf + band) in = exact_d2(kpos) <= cut;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const int slot = emitted + __popc(bal & ((1u << lane) - 1u));
+        if (in && slot < k_nn) out[slot] = __float_as_int(__ldg(sorted + kpos).w);
+        emitted += __popc(bal);
+      });
+      break;
     }
     if (lane == 0) {
       if (emitted > k_nn) { atomicOr(flags, 2); emitted = k_nn; }   // ties beyond k: list truncated
