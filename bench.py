@@ -225,6 +225,9 @@ def run_ours(args):
         t = torch.tensor([ms, e2e_s * 1e3, pp_ms], dtype=torch.float64, device="cuda")
         td.all_reduce(t, op=td.ReduceOp.MAX)
         ms, e2e_s, pp_ms = float(t[0]), float(t[1]) / 1e3, float(t[2])
+    if world > 1:
+        td.barrier()
+        td.destroy_process_group()
     if rank != 0:
         return
     total_scans = B * world * args.steps

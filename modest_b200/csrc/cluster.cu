@@ -205,6 +205,7 @@ __device__ __forceinline__ bool kth_by_histogram(Scan scan, int k_nn, T R2, int*
         have += __popc(bal);
       });
       if (inbin > 32 && lane == 0) atomicOr(flags, 1);          // unresolved tie block
+      if (have == 1) { *rk2 = __shfl_sync(0xffffffffu, mine, 0); return true; }
       int rank = 0;
       for (int l2 = 0; l2 < 32; ++l2) {
         const T v = __shfl_sync(0xffffffffu, mine, l2);
@@ -224,7 +225,9 @@ __device__ __forceinline__ bool kth_by_histogram(Scan scan, int k_nn, T R2, int*
 }
 
 constexpr int kKnnWarps = 4;
-constexpr int kListCap = 640;      // (f32 d2, sorted position) pairs cached per warp between the passes
+constexpr int kMaxLevels = 4;
+struct KnnLevels { int n; int L[kMaxLevels]; double r2[kMaxLevels]; };   // windows of +-L cells, radius^2 they cover
+constexpr int kListCap = 1024;      // (f32 d2, sorted position) pairs cached per warp between the passes
 
 // One warp per point.  Pass A sweeps the cell window once, evaluating d2 in float32 and caching
 // (d2, position) of everything inside the window radius in shared memory.  The k-th smallest
@@ -235,7 +238,7 @@ constexpr int kListCap = 640;      // (f32 d2, sorted position) pairs cached per
 // sets are therefore exactly those of the all-f64 algorithm (kept as the overflow fallback).
 __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
     const float4* __restrict__ sorted_all, const int* __restrict__ cells_all, const GridMeta* __restrict__ meta,
-    const int64_t* __restrict__ off, int G, int k_nn, double r2_max, int L_fine, double r2_fine, int L_coarse,
+    const int64_t* __restrict__ off, int G, int k_nn, double r2_max, KnnLevels lv,
     double* __restrict__ rk2_all, int32_t* __restrict__ knn_all, int32_t* __restrict__ knn_cnt_all,
     int32_t* __restrict__ flags) {
   const int s = blockIdx.y;
@@ -264,14 +267,16 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
       const float4 q = __ldg(sorted + kpos);
       return sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z);
     };
-    for (int level = 0; level < 2; ++level) {
-      const int L = level == 0 ? L_fine : L_coarse;
-      const double R2 = level == 0 ? r2_fine : r2_max;
-      if (level == 0) {        // cheap reject: fewer than k+1 points in the whole fine window
+    for (int level = 0; level < lv.n; ++level) {
+      const int L = lv.L[level];
+      const double R2 = lv.r2[level];
+      const bool last = level == lv.n - 1;
+      if (!last) {             // cheap reject: fewer than k+1 points in the whole window
         const int xa = clampi(cx - L, 0, G - 1), xb = clampi(cx + L, 0, G - 1);
         const int ya = clampi(cy - L, 0, G - 1), yb = clampi(cy + L, 0, G - 1);
         int tot = 0;
-        for (int y = ya; y <= yb; ++y) tot += __ldg(cells + y * G + xb + 1) - __ldg(cells + y * G + xa);
+        if (ya + lane <= yb) tot = __ldg(cells + (ya + lane) * G + xb + 1) - __ldg(cells + (ya + lane) * G + xa);
+        tot = warp_sum(tot);                             // windows are at most 32 rows tall
         if (tot <= k_nn) continue;
       }
       // f32 evaluation error of d2 (coordinates up to ~1e2 m, d2 <= R2): a few ulps of d2 plus
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
           });
         };
         const bool found = kth_by_histogram<double>(scan_grid, k_nn, R2, hist, lane, &rk2, flags);
-        if (!found && level == 0) continue;
+        if (!found && !last) continue;
         const double cut = fmin(rk2, r2_max);
         scan_grid([&](bool live, double d2, int j) {
           const bool in = live && d2 <= cut;
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
       float v32 = 0.f;
       // fine level: only when k points are certainly inside the fine radius (the window then
       // provably holds the k nearest); radius level: whenever k candidates are cached
-      if (sure >= k_nn || (level == 1 && cnt >= k_nn)) {
+      if (sure >= k_nn || (last && cnt >= k_nn)) {
         // find the k-th smallest on the f32 keys, then exactly inside the band around it
         float v = 0.f;
         kth_by_histogram<float>(scan_list, k_nn, R2f_list, hist, lane, &v, flags);
@@ -355,15 +360,16 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
         if (n_band > 32) { if (lane == 0) atomicOr(flags, 1); }
         const int need = k_nn - n_low;                     // 1-based rank inside the band
         int rank = 0;
-        for (int l2 = 0; l2 < 32; ++l2) {
-          const double vv = __shfl_sync(0xffffffffu, mine, l2);
-          rank += (vv < mine) || (vv == mine && l2 < lane);
-        }
+        if (n_band > 1)
+          for (int l2 = 0; l2 < 32; ++l2) {
+            const double vv = __shfl_sync(0xffffffffu, mine, l2);
+            rank += (vv < mine) || (vv == mine && l2 < lane);
+          }
         const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < min(n_band, 32));
         if (hitl) rk2 = __shfl_sync(0xffffffffu, mine, __ffs(hitl) - 1);
         else if (lane == 0) atomicOr(flags, 1);
         cut = fmin(rk2, r2_max);
-      } else if (level == 0) {
+      } else if (!last) {
         continue;      // (also the borderline case: the radius level, whose window contains this one, decides)
       }
       // ---- emission from the list: sure-below, sure-above, or exact inside the band around cut ----
@@ -465,6 +471,46 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
     if (a < b) { int t = a; a = b; b = t; }       // a > b: hang the larger root under the smaller
     const int old = atomicCAS(&parent[a], a, b);
     if (old == a) return;
+  }
+}
+
+// Initial forest (ECL-CC style): every core point hangs under its smallest qualifying core
+// neighbour with a smaller index, then a few pointer-doubling sweeps shorten the chains, so the
+// union sweep below mostly finds "already together".
+__global__ void __launch_bounds__(256) dbscan_init_kernel(
+    const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, int k_nn, const int32_t* __restrict__ nbr,
+    const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt, double eps, const uint8_t* __restrict__ core,
+    int32_t* __restrict__ parent) {
+  const int s = blockIdx.y;
+  const int n = n_kept[s];
+  const int64_t base = off[s];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < n; i += nwarps) {
+    if (!core[base + i]) continue;
+    const int m = nbr_cnt[base + i];
+    const size_t row = (size_t)(base + i) * k_nn;
+    int best = i;
+    for (int c = lane; c < m; c += 32) {
+      const int j = nbr[row + c];
+      if (j < best && core[base + j] && (double)nbr_w[row + c] <= eps) best = j;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) parent[base + i] = best;
+  }
+}
+
+__global__ void __launch_bounds__(256) dbscan_jump_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept,
+                                                          int32_t* __restrict__ parent) {
+  const int s = blockIdx.y;
+  const int n = n_kept[s];
+  int32_t* par = parent + off[s];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int p = par[i];
+    int gp = par[p];
+    // parents only ever decrease, so a racing update can only shorten the path further
+    if (gp != p) { const int ggp = par[gp]; par[i] = ggp; }
   }
 }
 
@@ -615,12 +661,6 @@ extern "C" int modest_ground_mask_batch(const float* d_ptc, int point_stride, co
 static const float kGraphCell = 0.5f;        // fine cell edge of the kNN grid [m]
 static const float kGraphSlack = 1.001f;
 
-static int graph_levels(double radius, int* L_coarse) {
-  int L = (int)ceil(radius / (double)kGraphCell - 1e-9);
-  if (L < 1) L = 1;
-  *L_coarse = L;
-  return 1;   // fine level probes +-1 cell
-}
 
 extern "C" size_t modest_graph_workspace_bytes(int n_scans, int64_t n_points_total, int n_neighbors, int grid_dim) {
   if (grid_dim <= 0) grid_dim = 288;
@@ -662,18 +702,27 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
   const float cell = kGraphCell * kGraphSlack;
   int rc = grid2d_build(d_kept, 4, d_off, d_n_kept, n_scans, max_points, cell, G, meta, cells, sorted, stream);
   if (rc != MODEST_OK) return rc;
-  int L_coarse;
-  const int L_fine = graph_levels(radius, &L_coarse);
+  // search windows: +-1, +-2, ... cells (radius = window reach, capped at the graph radius); the
+  // last level always covers the full radius
+  KnnLevels lv;
+  lv.n = 0;
   const double r2_max = radius * radius;
-  double r_fine = (double)kGraphCell * L_fine;            // a ball of this radius fits the +-L_fine cell window
-  if (r_fine > radius) r_fine = radius;
-  const double r2_fine = r_fine * r_fine;
+  int L_full = (int)ceil(radius / (double)kGraphCell - 1e-9);
+  if (L_full < 1) L_full = 1;
+  for (int L = 1; L < L_full && lv.n < 1; L *= 2) {        // one fine level measured best (profiles/README.md)
+    lv.L[lv.n] = L;
+    lv.r2[lv.n] = ((double)kGraphCell * L) * ((double)kGraphCell * L);
+    ++lv.n;
+  }
+  lv.L[lv.n] = L_full;
+  lv.r2[lv.n] = r2_max;
+  ++lv.n;
   int wblocks = (int)((max_points + 3) / 4);
   if (wblocks < 1) wblocks = 1;
   if (wblocks > 148 * 16) wblocks = 148 * 16;
   MODEST_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t), stream));
   knn_select_kernel<<<dim3(wblocks, n_scans), kKnnWarps * 32, 0, stream>>>(sorted, cells, meta, d_off, G, n_neighbors, r2_max,
-                                                               L_fine, r2_fine, L_coarse, rk2, knn, knn_cnt, d_flags);
+                                                               lv, rk2, knn, knn_cnt, d_flags);
   MODEST_LAUNCH_CHECK("knn_select_kernel");
   int mblocks = (int)((max_points * 32 + 255) / 256);
   if (mblocks < 1) mblocks = 1;
@@ -714,6 +763,13 @@ extern "C" int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept
   int64_t eb = (max_points * 32 + 255) / 256;          // one warp per row
   if (eb < 1) eb = 1;
   if (eb > 148 * 16) eb = 148 * 16;
+  dbscan_init_kernel<<<dim3((unsigned)eb, n_scans), 256, 0, stream>>>(d_off, d_n_kept, n_neighbors, d_nbr, d_nbr_w,
+                                                                     d_nbr_cnt, eps, core, parent);
+  MODEST_LAUNCH_CHECK("dbscan_init_kernel");
+  for (int r = 0; r < 4; ++r) {
+    dbscan_jump_kernel<<<dim3(pblocks, n_scans), 256, 0, stream>>>(d_off, d_n_kept, parent);
+    MODEST_LAUNCH_CHECK("dbscan_jump_kernel");
+  }
   dbscan_union_kernel<<<dim3((unsigned)eb, n_scans), 256, 0, stream>>>(d_off, d_n_kept, n_neighbors, d_nbr, d_nbr_w,
                                                                       d_nbr_cnt, eps, core, parent);
   MODEST_LAUNCH_CHECK("dbscan_union_kernel");
@@ -728,6 +784,6 @@ extern "C" int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept
   MODEST_LAUNCH_CHECK("dbscan_label_borders_kernel");
   dbscan_merge_borders_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_n_kept, core, border_lab, d_labels_kept);
   MODEST_LAUNCH_CHECK("dbscan_merge_borders_kernel");
-  note_launch(6);
+  note_launch(11);
   return MODEST_OK;
 }
