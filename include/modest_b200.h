@@ -233,6 +233,29 @@ int modest_filter_and_fit_batch(const float* d_ptc, int point_stride, const int6
                                 int32_t* d_flags, void* d_ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * PP-score percentile of the scan points inside each box.
+ * Replaces the numeric part of filter_by_ppscore() (combine_labels.py:42-60): a point is
+ * inside when its rect (x,z), moved into the box frame, lies strictly inside (-l/2,l/2) x
+ * (-w/2,w/2) and t.y - h < y <= t.y; the percentile is numpy's float32 'linear' rule.
+ *   d_boxes (S,max_boxes,8) f64 rows t.x t.y t.z l w h ry (8th column ignored), d_n_boxes (S)
+ *   d_box_trig optional (S,max_boxes,2) f64: cos(ry), sin(ry) evaluated by the caller with the
+ *           host libm (what numpy gives the reference); NULL -> evaluated on the device
+ *   q_f32   percentile/100 evaluated in float32 by the caller
+ *   d_percentile (S,max_boxes) f32 out, d_count (S,max_boxes) i32 out (0 -> box holds no point)
+ * Rect coordinates come from d_rect_in when given, else from d_ptc + d_calib.
+ * Synchronises `stream` once (uploads a small offset table).
+ * ------------------------------------------------------------------------------------------ */
+size_t modest_box_pp_workspace_bytes(int n_scans, int64_t n_points_total, int64_t max_points,
+                                     int max_boxes);
+int modest_box_pp_percentile_batch(const float* d_ptc, int point_stride, const int64_t* d_off,
+                                   const float* d_pp, const double* d_calib,
+                                   const double* d_rect_in, const double* d_boxes,
+                                   const double* d_box_trig, const int32_t* d_n_boxes, int n_scans,
+                                   int64_t n_points_total, int64_t max_points, int max_boxes,
+                                   double q_f32, float* d_percentile, int32_t* d_count,
+                                   void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stage N: rotated BEV IoU / overlap / NMS on boxes [x, y, z, dx, dy, dz, heading] (f32).
  * Drop-in for the reference's pybind11 module iou3d_nms_cuda
  * (utils/iou3d_nms/src/iou3d_nms_api.cpp:11-17; host wrappers iou3d_nms.cpp:48-188;

@@ -50,6 +50,9 @@ SIGNATURES = {
     "modest_filter_and_fit_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _i64,
                                               C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp,
                                               _vp, _vp, _vp, _sz, _vp]),
+    "modest_box_pp_workspace_bytes": (_sz, [C.c_int, _i64, _i64, C.c_int]),
+    "modest_box_pp_percentile_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _i64, C.c_int,
+                                                 _f64, _vp, _vp, _vp, _sz, _vp]),
     "modest_boxes_iou_bev": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     "modest_boxes_overlap_bev": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp]),
     "modest_nms_workspace_bytes": (_sz, [C.c_int]),

@@ -606,6 +606,57 @@ __global__ void __launch_bounds__(256) apply_final_kernel(const int64_t* __restr
   }
 }
 
+
+// ---- f-1: PP-score percentile of the scan points inside each (detector) box ---------------------
+// filter_by_ppscore() of combine_labels.py:42-60: footprint test in the box frame (same dgemm
+// rounding as get_lowest_point_rect) AND t.y - h < y <= t.y, then np.percentile(pp[inside], q)
+// in numpy 2.x float32 arithmetic.  One CTA per box; pass 1 collects the member pp values into
+// a per-box slice of `vals` (capacity = points of the scan), pass 2 selects.
+__global__ void __launch_bounds__(256) box_pp_percentile_kernel(
+    const int64_t* __restrict__ off, const double* __restrict__ rect, const float* __restrict__ pp,
+    const double* __restrict__ boxes /* (S,max_boxes,8) t.x t.y t.z l w h ry _ */, const int32_t* __restrict__ n_boxes,
+    const double* __restrict__ box_trig /* (S,max_boxes,2) cos(ry), sin(ry) from the host libm, or NULL */,
+    int max_boxes, float q, float* __restrict__ vals /* (S,max_boxes) slices of N_s floats */,
+    const int64_t* __restrict__ vals_off /* (S) */, float* __restrict__ pct_out, int32_t* __restrict__ cnt_out) {
+  const int s = blockIdx.y, k = blockIdx.x;
+  if (k >= n_boxes[s]) return;
+  const int64_t beg = off[s];
+  const int n = (int)(off[s + 1] - beg);
+  const double* b = boxes + ((size_t)s * max_boxes + k) * 8;
+  const double tx = b[0], ty = b[1], tz = b[2], l = b[3], w = b[4], h = b[5], ry = b[6];
+  // numpy's cos/sin of ry when the caller supplies them (bit-faithful footprints), else libdevice's
+  const double c = box_trig ? box_trig[((size_t)s * max_boxes + k) * 2] : cos(ry);
+  const double sn = box_trig ? box_trig[((size_t)s * max_boxes + k) * 2 + 1] : sin(ry);
+  const double hl = __ddiv_rn(l, 2.0), hw = __ddiv_rn(w, 2.0), ylo = __dsub_rn(ty, h);
+  float* mine = vals + vals_off[s] + (size_t)k * n;
+  __shared__ int s_cnt;
+  __shared__ unsigned hist[256];
+  __shared__ unsigned sel[2];
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double x = rect[3 * (beg + i)], y = rect[3 * (beg + i) + 1], z = rect[3 * (beg + i) + 2];
+    const double dx = __dsub_rn(x, tx), dz = __dsub_rn(z, tz);
+    const double lx = __fma_rn(dz, -sn, __dmul_rn(dx, c));
+    const double ly = __fma_rn(dz, c, __dmul_rn(dx, sn));
+    if (lx > -hl && lx < hl && ly > -hw && ly < hw && y > ylo && y <= ty) mine[atomicAdd(&s_cnt, 1)] = pp[beg + i];
+  }
+  __syncthreads();
+  const int m = s_cnt;
+  float r = 0.f;
+  if (m > 0) {
+    const float vi = __fmul_rn((float)(m - 1), q);
+    const int lo = (int)floorf(vi);
+    const int hi = min(lo + 1, m - 1);
+    const float g = __fsub_rn(vi, (float)lo);
+    const float a = block256_kth_smallest(m, lo, [&](int i) { return mine[i]; }, hist, sel);
+    const float bb = hi == lo ? a : block256_kth_smallest(m, hi, [&](int i) { return mine[i]; }, hist, sel);
+    const float d = __fsub_rn(bb, a);
+    r = g >= 0.5f ? __fsub_rn(bb, __fmul_rn(d, __fsub_rn(1.0f, g))) : __fadd_rn(a, __fmul_rn(d, g));
+  }
+  if (threadIdx.x == 0) { pct_out[(size_t)s * max_boxes + k] = r; cnt_out[(size_t)s * max_boxes + k] = m; }
+}
+
 }  // namespace modest
 
 using namespace modest;
@@ -728,5 +779,50 @@ extern "C" int modest_filter_and_fit_batch(
   apply_final_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_labels_filtered, max_clusters, final_id, d_labels_final);
   MODEST_LAUNCH_CHECK("apply_final_kernel");
   note_launch(14);
+  return MODEST_OK;
+}
+
+extern "C" size_t modest_box_pp_workspace_bytes(int n_scans, int64_t n_points_total, int64_t max_points, int max_boxes) {
+  return align_up(sizeof(double) * 3 * (size_t)n_points_total, 256) + align_up(sizeof(CalibDev) * (size_t)n_scans, 256) +
+         align_up(sizeof(float) * (size_t)n_scans * max_boxes * (size_t)max_points, 256) +
+         align_up(sizeof(int64_t) * (size_t)n_scans, 256) + 1024;
+}
+
+extern "C" int modest_box_pp_percentile_batch(const float* d_ptc, int point_stride, const int64_t* d_off, const float* d_pp,
+                                              const double* d_calib, const double* d_rect_in, const double* d_boxes,
+                                              const double* d_box_trig, const int32_t* d_n_boxes, int n_scans, int64_t n_points_total, int64_t max_points,
+                                              int max_boxes, double q_f32, float* d_percentile, int32_t* d_count, void* d_ws,
+                                              size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_scans <= 0) return MODEST_OK;
+  MODEST_REQUIRE(d_ptc && d_off && d_pp && (d_calib || d_rect_in) && d_boxes && d_n_boxes && d_percentile && d_count && d_ws,
+                 "box_pp_percentile: null pointer argument");
+  MODEST_REQUIRE(max_boxes >= 1 && n_scans <= 65535, "box_pp_percentile: bad sizes");
+  MODEST_REQUIRE(ws_bytes >= modest_box_pp_workspace_bytes(n_scans, n_points_total, max_points, max_boxes),
+                 "box_pp_percentile: workspace too small");
+  Arena ar(d_ws, ws_bytes);
+  double* rect_ws = ar.take<double>(3 * (size_t)n_points_total);
+  CalibDev* calibs = ar.take<CalibDev>(n_scans);
+  float* vals = ar.take<float>((size_t)n_scans * max_boxes * (size_t)max_points);
+  int64_t* vals_off = ar.take<int64_t>(n_scans);
+  const double* rect = d_rect_in ? d_rect_in : rect_ws;
+  int pblocks = (int)((max_points + 255) / 256);
+  if (pblocks < 1) pblocks = 1;
+  if (!d_rect_in) {
+    MODEST_CUDA(cudaMemcpyAsync(calibs, d_calib, sizeof(CalibDev) * (size_t)n_scans, cudaMemcpyDeviceToDevice, stream));
+    rect_coords_kernel<<<dim3(pblocks, n_scans), 256, 0, stream>>>(d_ptc, point_stride, d_off, calibs, rect_ws);
+    MODEST_LAUNCH_CHECK("rect_coords_kernel");
+  }
+  // slice s starts at s * max_boxes * max_points (host-computed, uploaded once per call)
+  {
+    static thread_local int64_t h_off[65536];
+    for (int s = 0; s < n_scans; ++s) h_off[s] = (int64_t)s * max_boxes * max_points;
+    MODEST_CUDA(cudaMemcpyAsync(vals_off, h_off, sizeof(int64_t) * (size_t)n_scans, cudaMemcpyHostToDevice, stream));
+    MODEST_CUDA(cudaStreamSynchronize(stream));      // h_off is reused by the next call
+  }
+  box_pp_percentile_kernel<<<dim3(max_boxes, n_scans), 256, 0, stream>>>(d_off, rect, d_pp, d_boxes, d_n_boxes, d_box_trig, max_boxes,
+                                                                        (float)q_f32, vals, vals_off, d_percentile, d_count);
+  MODEST_LAUNCH_CHECK("box_pp_percentile_kernel");
+  note_launch(d_rect_in ? 1 : 2);
   return MODEST_OK;
 }

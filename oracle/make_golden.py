@@ -197,6 +197,47 @@ def main():
                                         cfg["plane_estimate"]["range"], return_model=True)
         ransac_same_trials = bool(rr["n_trials"] == model.n_trials_)
         ransac_mask_diff = int((rr["inlier_mask"] != model.inlier_mask_).sum())
+        # ---------------- f-1: combine_labels on synthetic detections ----------------
+        drng = np.random.default_rng(4242 + case.scan_id)
+        nd = len(R["objs"])
+        loc = np.array([o.t for o in R["objs"]]).reshape(-1, 3) + drng.normal(0, 0.15, (nd, 3))
+        dims = np.array([[o.l, o.h, o.w] for o in R["objs"]]).reshape(-1, 3) * drng.uniform(0.9, 1.15, (nd, 3))
+        rys = np.array([o.ry for o in R["objs"]]) + drng.normal(0, 0.05, nd)
+        n_fp = 12                                            # false positives on static structure / empty space
+        rect_all = R["calib"].project_velo_to_rect(case.query[:, :3])
+        fp_c = rect_all[drng.choice(len(rect_all), n_fp, replace=False)]
+        loc = np.concatenate([loc, fp_c + np.array([0, 0.8, 0])])
+        dims = np.concatenate([dims, np.column_stack([drng.uniform(3, 5, n_fp), drng.uniform(1.4, 2, n_fp), drng.uniform(1.5, 2.2, n_fp)])])
+        rys = np.concatenate([rys, drng.uniform(-3, 3, n_fp)])
+        preds = dict(frame_id="%06d" % case.scan_id, location=loc, dimensions=dims, rotation_y=rys,
+                     score=drng.uniform(-0.5, 1.0, len(loc)))
+        import copy
+        ref_gate = np.array([ref.cb.filter_by_ppscore(rect_all, pp, o, percentile=50, threshold=0.5)
+                             for o in ref.cb.predicts2objs(preds)])
+        orc_gate = np.array([orc.detection_passes_pp_gate(rect_all, pp, o) for o in orc.detections_to_boxes(preds)])
+        assert np.array_equal(ref_gate, orc_gate), "pp gate restatement"
+        det_obj = [o for o, k in zip(ref.cb.predicts2objs(preds), ref_gate) if k & (o.score > -1)]
+        gen_obj = copy.deepcopy(R["objs"])
+        ref.cb.add_area_score(gen_obj)
+        objs_all = det_obj + gen_obj
+        import torch
+        from oracle import build_ref
+        ext = build_ref.load_cpu()
+        bt = torch.from_numpy(np.array([[o.t[0], o.t[2], 0, o.l, o.w, o.h, -o.ry] for o in objs_all])).float()
+        iou_m = torch.zeros((len(objs_all), len(objs_all)))
+        ext.boxes_iou_bev_cpu(bt.contiguous(), bt.contiguous(), iou_m)
+        iou_m = iou_m.numpy()
+        keep_m = np.ones(len(objs_all), dtype=bool)
+        for i_ in np.argsort([o.score for o in objs_all])[::-1]:        # objs_nms(use_score_rank=True)
+            if keep_m[i_]:
+                keep_m[iou_m[i_] > 0.1] = False
+                keep_m[i_] = True
+        merged = [o for o, k in zip(objs_all, keep_m) if k]
+        merged = [o for o in merged if ref.pc.is_within_fov(o, R["calib"], list(shape.image_shape))]
+        merge_text = ref.pc.objs2label(merged, R["calib"], with_score=True)
+        o_text, _ = orc.merge_labels_for_scan(preds, copy.deepcopy(R["objs"]), rect_all, pp, orc.Calib(R["calib_path"]),
+                                              lambda b: iou_m, image_shape=shape.image_shape, with_score=True)
+        assert o_text == merge_text, "merge text restatement"
         g_sorted = g.copy()
         g_sorted.sort_indices()
         np.savez_compressed(
@@ -211,7 +252,9 @@ def main():
             inlier_count1=int(model.inlier_mask_.sum()), thr1=np.float32(orc.mad_threshold(sel[:, 2])),
             calib_P2=np.asarray(case.calib["P2"]), calib_V2C=np.asarray(case.calib["Tr_velo_to_cam"]),
             calib_R0=np.asarray(case.calib["R0_rect"]), image_shape=np.array(shape.image_shape),
-            max_hs=shape.max_hs)
+            max_hs=shape.max_hs, det_location=preds["location"], det_dimensions=preds["dimensions"],
+            det_rotation_y=preds["rotation_y"], det_score=preds["score"], det_pp_gate=ref_gate,
+            merge_iou_cpu=iou_m, merge_text=merge_text)
         meta["cases"][name] = dict(n_points=N, n_kept=int(R["final_mask"].sum()), graph_nnz=int(g.nnz),
                                    n_clusters_raw=int(R["labels_raw"].max() + 1), n_boxes=len(R["objs"]),
                                    n_labels=R["label_text"].count("\n") + (1 if R["label_text"] else 0),

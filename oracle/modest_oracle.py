@@ -650,6 +650,47 @@ def kitti_label_text(objs, calib, obj_type="Dynamic", with_score=False):
 
 
 # ------------------------------------------------------------------------------------------
+# f-1  self-training merge (combine_labels.py)
+# ------------------------------------------------------------------------------------------
+def detections_to_boxes(preds):
+    """combine_labels.py:23-34 -- dimensions are stored (l, h, w)."""
+    out = []
+    for i in range(preds["location"].shape[0]):
+        d = preds["dimensions"][i]
+        out.append(types.SimpleNamespace(t=preds["location"][i], l=d[0], h=d[1], w=d[2],
+                                         ry=preds["rotation_y"][i], score=preds["score"][i]))
+    return out
+
+
+def detection_passes_pp_gate(rect, pp, obj, percentile=50, threshold=0.5):
+    """combine_labels.py:42-60 -- PP percentile of the points inside the box (rotated footprint,
+    t.y - h < y <= t.y) must not exceed the threshold; an empty box fails."""
+    c, s = np.cos(obj.ry), np.sin(obj.ry)
+    local = (rect[:, [0, 2]] - obj.t[[0, 2]]) @ np.array([[c, -s], [s, c]]).T
+    inside = (np.abs(local[:, 0]) < obj.l / 2) & (np.abs(local[:, 1]) < obj.w / 2)
+    inside &= (rect[:, 1] > obj.t[1] - obj.h) & (rect[:, 1] <= obj.t[1])
+    return bool(inside.sum() > 0 and not (np.percentile(pp[inside], percentile) > threshold))
+
+
+def merge_labels_for_scan(preds, seed_objs, rect, pp, calib, iou_fn, image_shape=(1024, 1224), percentile=50,
+                          threshold=0.5, score_filtering=-1, nms_threshold=0.1, fov_only=True, with_score=False):
+    """combine_labels.py:101-121 for one frame."""
+    dets = [o for o in detections_to_boxes(preds)
+            if detection_passes_pp_gate(rect, pp, o, percentile, threshold) & (o.score > score_filtering)]
+    for o in seed_objs:
+        o.score = -999 + o.w * o.l                                   # add_area_score, :37-39
+    objs = dets + list(seed_objs)
+    if objs:
+        iou = iou_fn(boxes_for_nms(objs))
+        order = np.argsort([o.score for o in objs])[::-1]
+        keep = greedy_suppress(iou, order, nms_threshold)
+        objs = [o for o, k in zip(objs, keep) if k]
+    if fov_only:
+        objs = [o for o in objs if box_in_fov(o, calib, image_shape)]
+    return kitti_label_text(objs, calib, with_score=with_score), objs
+
+
+# ------------------------------------------------------------------------------------------
 # Whole-scan drivers (the bodies of the three CLI loops)
 # ------------------------------------------------------------------------------------------
 DEFAULT_MASK_CFG = dict(

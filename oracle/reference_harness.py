@@ -117,9 +117,10 @@ def load():
         from utils import clustering_utils as ref_cl    # noqa
         from utils import kitti_util as ref_ku          # noqa
         import generate_mask as ref_gm                  # noqa
+        import combine_labels as ref_cb                 # noqa
     finally:
         sys.path.remove(_GCM)
-    ns = types.SimpleNamespace(pp=ref_pp, pc=ref_pc, cl=ref_cl, ku=ref_ku, gm=ref_gm, AttrDict=_AttrDict)
+    ns = types.SimpleNamespace(pp=ref_pp, pc=ref_pc, cl=ref_cl, ku=ref_ku, gm=ref_gm, cb=ref_cb, AttrDict=_AttrDict)
     # keep the reference's `utils` package from shadowing anything of ours
     ns._mods = {k: sys.modules.pop(k) for k in list(sys.modules)
                 if k == "utils" or k.startswith("utils.")}

@@ -324,3 +324,104 @@ def test_streaming_engine_matches_direct_calls(golden_case):
         r = pipe.run(sb, rng="device", seed=5 + step)
         assert pipe.label_texts(sb, r.boxes, r.n_boxes, r.keep) == texts
     assert any(t for _, ts in got for t in ts)
+
+
+def test_edge_cases_empty_ragged_and_degenerate():
+    """Empty / tiny / clusterless scans in one ragged batch; empty traversals; far outliers."""
+    from oracle import modest_oracle as orc
+    from modest_b200 import synth
+    rng = np.random.default_rng(0)
+    # --- PP: ragged batch with an empty query, an empty traversal and far-away points ---
+    q0 = rng.uniform(-5, 5, (300, 3)).astype(np.float32)
+    q1 = np.zeros((0, 3), np.float32)
+    q2 = np.concatenate([rng.uniform(-3, 3, (200, 3)), [[500.0, -800.0, 40.0], [-300.0, 900.0, -60.0]]]).astype(np.float32)
+    h0 = [q0[:150] + rng.normal(0, 0.05, (150, 3)).astype(np.float32), np.zeros((0, 3), np.float32),
+          rng.uniform(-5, 5, (400, 3)).astype(np.float32)]
+    h1 = [rng.uniform(-1, 1, (10, 3)).astype(np.float32), rng.uniform(-1, 1, (5, 3)).astype(np.float32)]
+    h2 = [q2[::2] + np.float32(0.1), q2[1::2].copy(), np.array([[500.2, -800.0, 40.0]], np.float32), q2.copy()]
+    b = pp_score.pack_batch([q0, q1, q2], [h0, h1, h2])
+    counts = torch.zeros(b.n_count_total, dtype=torch.int32, device="cuda")
+    pp = pp_score.PPScorer()(b, counts=counts).cpu().numpy()
+    counts = counts.cpu().numpy()
+    for s, (q, h) in enumerate([(q0, h0), (q1, h1), (q2, h2)]):
+        ref = orc.neighbor_counts_bruteforce(q, h) if len(q) else np.zeros((0, len(h)), np.int64)
+        got = counts[b.h_count_off[s]:b.h_count_off[s + 1]].reshape(len(q), len(h))
+        assert np.array_equal(got, ref)
+        if len(q):
+            want = orc.persistence_entropy(ref).astype(np.float32)
+            assert np.allclose(pp[b.h_q_off[s]:b.h_q_off[s + 1]], want, atol=1e-6, equal_nan=True)
+    # --- pipeline: a normal scan, a scan with no points, a scan that is ground only ---
+    case = synth.make_scan_case(21, synth.LYFT, n_traversals=2, n_points=5000)
+    g = rng.uniform(-30, 30, (3000, 2))
+    ground = np.column_stack([g, -1.8 + rng.normal(0, 0.01, 3000), rng.uniform(0, 1, 3000)]).astype(np.float32)
+    ptcs = [case.query, np.zeros((0, 4), np.float32), ground]
+    pps = [rng.uniform(0, 1, 5000).astype(np.float32), np.zeros(0, np.float32), np.ones(3000, np.float32)]
+    p = pl.SeedLabelPipeline()
+    sb = pl.make_batch(ptcs, pps, [case.calib] * 3)
+    r = p.run(sb, rng="device", seed=1)
+    torch.cuda.synchronize()
+    nb = r.n_boxes.cpu().numpy()
+    lab = r.labels.cpu().numpy()
+    assert nb[1] == 0 and nb[2] == 0
+    assert (lab[sb.h_off[2]:sb.h_off[3]] == 0).all()
+    texts = p.label_texts(sb, r.boxes, r.n_boxes, r.keep)
+    assert texts[1] == "" and texts[2] == ""
+    single = p.run(pl.make_batch([case.query], [pps[0]], [case.calib]), rng="device", seed=1)
+    assert np.array_equal(single.labels.cpu().numpy(), lab[:5000])
+
+
+def test_iou_and_nms_edge_cases():
+    from modest_b200.generate_cluster_mask.utils.iou3d_nms import iou3d_nms_utils as ours
+    e = torch.zeros((0, 7), device="cuda")
+    one = torch.tensor([[0., 0, 0, 4, 2, 1.5, 0.3]], device="cuda")
+    assert ours.boxes_iou_bev(e, one).shape == (0, 1) and ours.boxes_iou_bev(one, e).shape == (1, 0)
+    assert abs(float(ours.boxes_iou_bev(one, one)) - 1.0) < 1e-5
+    far = torch.tensor([[100., 100, 0, 4, 2, 1.5, 0.3]], device="cuda")
+    assert float(ours.boxes_iou_bev(one, far)) == 0.0
+    keep, _ = ours.nms_gpu(torch.cat([one, one, far]), torch.tensor([0.9, 0.8, 0.7], device="cuda"), 0.1)
+    assert keep.tolist() == [0, 2]
+    keep, _ = ours.nms_gpu(e, torch.zeros(0, device="cuda"), 0.1)
+    assert keep.numel() == 0
+    iou3d = ours.boxes_iou3d_gpu(one, one)
+    assert abs(float(iou3d) - 1.0) < 1e-5
+    assert np.allclose(ours.boxes_bev_iou_cpu(one.cpu().numpy(), one.cpu().numpy()), 1.0, atol=1e-5)
+    big = torch.rand((700, 7), device="cuda") * torch.tensor([40, 40, 0, 4, 2, 1, 3.0], device="cuda") + \
+        torch.tensor([0, 0, 0, 0.5, 0.5, 1, 0], device="cuda")
+    k1, _ = ours.nms_gpu(big, torch.rand(700, device="cuda"), 0.3, pre_maxsize=500)
+    assert 0 < k1.numel() <= 500
+
+
+@pytest.mark.parametrize("name", ["small", "nusc_small", "lyft60k_t2"])
+def test_combine_labels_merge(golden_case, name, tmp_path):
+    """the drop-in combine_labels program against the reference's functions
+    (filter_by_ppscore / predicts2objs / add_area_score + score-ranked NMS + with_score labels)."""
+    import os
+    import pickle
+    from modest_b200 import synth
+    from modest_b200.generate_cluster_mask import combine_labels as cb
+    from modest_b200.generate_cluster_mask.utils import kitti_util as ku
+    from modest_b200.generate_cluster_mask.utils import pointcloud_utils as pu
+    case, shape, g = golden_case(name)
+    cal = ku.Calibration(dict(P2=g["calib_P2"], Tr_velo_to_cam=g["calib_V2C"], R0_rect=g["calib_R0"]))
+    rect = cal.project_velo_to_rect(case.query[:, :3])
+    preds = dict(frame_id="%06d" % case.scan_id, location=g["det_location"], dimensions=g["det_dimensions"],
+                 rotation_y=g["det_rotation_y"], score=g["det_score"])
+    pct, cnt = cb.in_box_pp_percentile(rect, g["pp"], cb.predicts2objs(preds), 50)
+    gate = (cnt > 0) & ~(pct > np.float32(0.5))
+    assert np.array_equal(gate, g["det_pp_gate"])
+    assert cb.filter_by_ppscore(rect, g["pp"], cb.predicts2objs(preds)[0]) == bool(g["det_pp_gate"][0])
+    # the whole program on files
+    root = tmp_path / "data"
+    for d in ("velodyne", "calib"):
+        os.makedirs(root / d)
+    idx = case.scan_id
+    case.query.tofile(root / "velodyne" / f"{idx:06d}.bin")
+    synth.write_calib(str(root / "calib" / f"{idx:06d}.txt"), case.calib)
+    os.makedirs(tmp_path / "pp"); os.makedirs(tmp_path / "bbox")
+    np.save(tmp_path / "pp" / f"{idx:06d}.npy", g["pp"])
+    pickle.dump([pu.box_namespace(r) for r in g["boxes"]], open(tmp_path / "bbox" / f"{idx:06d}.pkl", "wb"))
+    pickle.dump([preds], open(tmp_path / "result.pkl", "wb"))
+    cfg = _cli_cfg("combine_labels.yaml", str(root), str(tmp_path), det_result_path=str(tmp_path / "result.pkl"),
+                   save_path=str(tmp_path / "out"), with_score=True, image_shape=list(shape.image_shape))
+    cb.main(cfg)
+    assert (tmp_path / "out" / f"{idx:06d}.txt").read_text() == str(g["merge_text"])

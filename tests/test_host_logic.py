@@ -90,7 +90,7 @@ def test_reference_config_keys_are_all_present():
     if not os.path.isdir(ref_dir):
         pytest.skip("reference tree not present")
     ours = os.path.join(ROOT, "modest_b200", "generate_cluster_mask", "configs")
-    for rel in ("pp_score.yaml", "generate_mask.yaml", "generate_label_files.yaml", "data_paths/fw70_2m.yaml",
+    for rel in ("pp_score.yaml", "generate_mask.yaml", "generate_label_files.yaml", "combine_labels.yaml", "data_paths/fw70_2m.yaml",
                 "data_paths/nusc.yaml"):
         a = yaml.safe_load(open(os.path.join(ref_dir, rel)))
         b = yaml.safe_load(open(os.path.join(ours, rel)))
