@@ -5,7 +5,7 @@ the same stages one scan at a time for RNG parity).  It overlaps the three phase
 batches on two CUDA streams:
 
     copy stream    : pinned host -> device copies of batch k+1
-    compute stream : PP score + seed-label pipeline of batch k
+    compute streams: PP score + seed-label pipeline of batch k (two lanes, alternating batches)
     host           : device -> host copy of the (small) box tables of batch k-1 and label text
 
 Inputs per scan are what the reference's programs hold in memory just before their numeric
@@ -61,10 +61,15 @@ def make_host_batch(queries_fixed, histories, ptcs, calibs, scan_ids=None) -> Ho
 class _Slot:
     """Device-side staging for one in-flight batch."""
 
-    def __init__(self):
+    def __init__(self, cfg, radius, grid_dim, max_clusters, max_boxes):
         self.bufs = {}
         self.ready = torch.cuda.Event()
         self.done = torch.cuda.Event()
+        # every slot is a complete lane (own stream, workspaces and scratch), so the kernels of
+        # consecutive batches can overlap: one batch's narrow kernels fill the other's gaps
+        self.stream = torch.cuda.Stream()
+        self.pipe = pl.SeedLabelPipeline(cfg, max_clusters=max_clusters, max_boxes=max_boxes)
+        self.scorer = pp_mod.PPScorer(radius=radius, grid_dim=grid_dim)
         self.pp_batch = None
         self.scan_batch = None
         self.result = None
@@ -88,11 +93,9 @@ class _Slot:
 
 class SeedLabelEngine:
     def __init__(self, cfg=None, radius=0.3, grid_dim=512, max_clusters=2048, max_boxes=128, seed=0):
-        self.pipe = pl.SeedLabelPipeline(cfg, max_clusters=max_clusters, max_boxes=max_boxes)
-        self.scorer = pp_mod.PPScorer(radius=radius, grid_dim=grid_dim)
         self.copy_stream = torch.cuda.Stream()
-        self.compute_stream = torch.cuda.Stream()
-        self.slots = [_Slot(), _Slot()]
+        self.slots = [_Slot(cfg, radius, grid_dim, max_clusters, max_boxes) for _ in range(2)]
+        self.pipe = self.slots[0].pipe
         self.seed = int(seed)
         self.d2h_bytes_last = 0
 
@@ -135,10 +138,10 @@ class SeedLabelEngine:
 
     # ---- stage 2: kernels on the compute stream ---------------------------------------------------
     def _compute(self, slot: _Slot, step: int):
-        with torch.cuda.stream(self.compute_stream):
-            self.compute_stream.wait_event(slot.ready)
-            self.scorer(slot.pp_batch, out=slot.scan_batch.pp, stream=self.compute_stream)
-            slot.result = self.pipe.run(slot.scan_batch, rng="device", seed=self.seed + step, stream=self.compute_stream)
+        with torch.cuda.stream(slot.stream):
+            slot.stream.wait_event(slot.ready)
+            slot.scorer(slot.pp_batch, out=slot.scan_batch.pp, stream=slot.stream)
+            slot.result = slot.pipe.run(slot.scan_batch, rng="device", seed=self.seed + step, stream=slot.stream)
             r = slot.result
             # small results to pinned host memory, still on the compute stream
             r.h_boxes = slot.pinned("h_boxes", r.boxes.shape, torch.float64)
@@ -147,7 +150,7 @@ class SeedLabelEngine:
             r.h_boxes.copy_(r.boxes, non_blocking=True)
             r.h_n.copy_(r.n_boxes, non_blocking=True)
             r.h_keep.copy_(r.keep, non_blocking=True)
-            slot.done.record(self.compute_stream)
+            slot.done.record(slot.stream)
 
     # ---- stage 3: label text on the host ----------------------------------------------------------
     def _finish(self, slot: _Slot):
