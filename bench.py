@@ -233,6 +233,17 @@ def run_ours(args):
     n_boxes = int(res.n_boxes.sum().item())
 
     # ---- e2e (host buffers in, label text out)
+    # raw pinned host -> device bandwidth of this box, for context next to the e2e number
+    probe = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
+    probe_d = torch.empty_like(probe, device="cuda")
+    probe_d.copy_(probe, non_blocking=True)
+    torch.cuda.synchronize()
+    tp = time.perf_counter()
+    for _ in range(4):
+        probe_d.copy_(probe, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * probe.numel() * 4 / (time.perf_counter() - tp) / 1e9
+    del probe, probe_d
     e2e_run(2)
     barrier()
     t0 = time.perf_counter()
@@ -265,7 +276,8 @@ def run_ours(args):
                    "boxes_last_step": n_boxes},
         "clocks": clocks,
         "e2e": {"value": total_scans / e2e_s, "unit": "scans/s", "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": int(d2h_bytes[0])},
+                "d2h_bytes_per_step": int(d2h_bytes[0]), "h2d_link_gbs_measured": round(h2d_gbs, 1),
+                "h2d_gbs_used": round(h2d_bytes * args.steps / e2e_s / 1e9, 1)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "pp_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

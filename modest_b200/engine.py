@@ -94,7 +94,9 @@ class _Slot:
 class SeedLabelEngine:
     def __init__(self, cfg=None, radius=0.3, grid_dim=512, max_clusters=2048, max_boxes=128, seed=0):
         self.copy_stream = torch.cuda.Stream()
-        self.slots = [_Slot(cfg, radius, grid_dim, max_clusters, max_boxes) for _ in range(2)]
+        # three slots: while batch k computes, batch k+1 uploads and batch k-1 is read back, and
+        # no slot is refilled before the host has finished with its previous contents
+        self.slots = [_Slot(cfg, radius, grid_dim, max_clusters, max_boxes) for _ in range(3)]
         self.pipe = self.slots[0].pipe
         self.seed = int(seed)
         self.d2h_bytes_last = 0
@@ -103,12 +105,6 @@ class SeedLabelEngine:
     def _upload(self, slot: _Slot, hb: HostBatch):
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot.done)                # buffers free again?
-            q = slot.buf("q", hb.query_xyz.shape, torch.float32)
-            h = slot.buf("h", hb.hist_xyz.shape, torch.float32)
-            p = slot.buf("p", hb.ptc.shape, torch.float32)
-            q.copy_(hb.query_xyz, non_blocking=True)
-            h.copy_(hb.hist_xyz, non_blocking=True)
-            p.copy_(hb.ptc, non_blocking=True)
             q_sizes = hb.q_sizes
             trav_counts = [len(t) for t in hb.trav_sizes]
             h_sizes = [m for t in hb.trav_sizes for m in t]
@@ -117,14 +113,28 @@ class SeedLabelEngine:
             trav_off = np.concatenate([[0], np.cumsum(trav_counts)]).astype(np.int32)
             count_off = np.concatenate([[0], np.cumsum(np.array(q_sizes, np.int64) * np.array(trav_counts, np.int64))]).astype(np.int64)
             small = np.concatenate([q_off, h_off, count_off]).astype(np.int64)
-            small_d = slot.buf("off", small.shape, torch.int64)
-            small_d.copy_(torch.from_numpy(small), non_blocking=False)
-            trav_d = slot.buf("trav", trav_off.shape, torch.int32)
-            trav_d.copy_(torch.from_numpy(trav_off), non_blocking=False)
-            a, b = len(q_off), len(q_off) + len(h_off)
             crow = np.stack([pl.calib_row(c) for c in hb.calibs])
+            # the small tables go first and from pinned staging, so that enqueueing this upload
+            # never blocks the host behind the bulk copies
+            small_h = slot.pinned("off_h", small.shape, torch.int64)
+            trav_h = slot.pinned("trav_h", trav_off.shape, torch.int32)
+            calib_h = slot.pinned("calib_h", crow.shape, torch.float64)
+            small_h.copy_(torch.from_numpy(small))
+            trav_h.copy_(torch.from_numpy(trav_off))
+            calib_h.copy_(torch.from_numpy(crow))
+            small_d = slot.buf("off", small.shape, torch.int64)
+            trav_d = slot.buf("trav", trav_off.shape, torch.int32)
             calib_d = slot.buf("calib", crow.shape, torch.float64)
-            calib_d.copy_(torch.from_numpy(crow), non_blocking=False)
+            small_d.copy_(small_h, non_blocking=True)
+            trav_d.copy_(trav_h, non_blocking=True)
+            calib_d.copy_(calib_h, non_blocking=True)
+            q = slot.buf("q", hb.query_xyz.shape, torch.float32)
+            h = slot.buf("h", hb.hist_xyz.shape, torch.float32)
+            p = slot.buf("p", hb.ptc.shape, torch.float32)
+            q.copy_(hb.query_xyz, non_blocking=True)
+            h.copy_(hb.hist_xyz, non_blocking=True)
+            p.copy_(hb.ptc, non_blocking=True)
+            a, b = len(q_off), len(q_off) + len(h_off)
             slot.pp_batch = pp_mod.PPBatch(
                 q, small_d[:a], h, small_d[a:b], trav_d, small_d[b:], n_scans=len(q_sizes), n_trav_total=int(trav_off[-1]),
                 n_query_total=int(q_off[-1]), n_count_total=int(count_off[-1]), max_query_points=max(q_sizes),
@@ -170,12 +180,12 @@ class SeedLabelEngine:
             return
         self._upload(self.slots[0], nxt)
         while nxt is not None:
-            cur_slot = self.slots[step % 2]
+            cur_slot = self.slots[step % 3]
             cur = nxt
             nxt = next(it, None)
             self._compute(cur_slot, step)
             if nxt is not None:
-                self._upload(self.slots[(step + 1) % 2], nxt)
+                self._upload(self.slots[(step + 1) % 3], nxt)
             if pending is not None:
                 yield pending.host.scan_ids, self._finish(pending)
             pending = cur_slot

@@ -305,22 +305,24 @@ def test_transform_and_nusc_center_removal():
 
 
 def test_streaming_engine_matches_direct_calls(golden_case):
-    """SeedLabelEngine.process (two-stream overlap, pinned staging) == the stage calls made directly."""
+    """SeedLabelEngine.process (multi-stream overlap, pinned staging) == the stage calls made directly,
+    for a stream of DIFFERENT batches."""
     from modest_b200 import engine as eng
-    cases = [golden_case(n)[0] for n in ("small", "nusc_small")]
-    hb = eng.make_host_batch([c.query_fixed for c in cases], [c.history for c in cases], [c.query for c in cases],
-                             [c.calib for c in cases], scan_ids=[10, 11])
+    a, b_ = golden_case("small")[0], golden_case("nusc_small")[0]
+    groups = [[a, b_], [b_], [a], [b_, a], [a, b_]]
+    hbs = [eng.make_host_batch([c.query_fixed for c in g], [c.history for c in g], [c.query for c in g],
+                               [c.calib for c in g], scan_ids=[100 * k + i for i in range(len(g))])
+           for k, g in enumerate(groups)]
     e = eng.SeedLabelEngine(seed=5)
-    got = list(e.process([hb, hb, hb]))
-    assert [ids for ids, _ in got] == [[10, 11]] * 3
-    # direct: same kernels, same device RNG seeds (seed + step)
+    got = list(e.process(hbs))
+    assert [ids for ids, _ in got] == [hb.scan_ids for hb in hbs]
     scorer = pp_score.PPScorer()
     pipe = pl.SeedLabelPipeline()
-    for step, (_, texts) in enumerate(got):
-        b = pp_score.pack_batch([c.query_fixed for c in cases], [c.history for c in cases])
+    for step, ((_, texts), g) in enumerate(zip(got, groups)):
+        b = pp_score.pack_batch([c.query_fixed for c in g], [c.history for c in g])
         pp = scorer(b)
-        sb = pl.make_batch([c.query for c in cases], [pp[b.h_q_off[s]:b.h_q_off[s + 1]] for s in range(2)],
-                           [c.calib for c in cases])
+        sb = pl.make_batch([c.query for c in g], [pp[b.h_q_off[s]:b.h_q_off[s + 1]] for s in range(len(g))],
+                           [c.calib for c in g])
         r = pipe.run(sb, rng="device", seed=5 + step)
         assert pipe.label_texts(sb, r.boxes, r.n_boxes, r.keep) == texts
     assert any(t for _, ts in got for t in ts)
