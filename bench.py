@@ -268,7 +268,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 tests + f64 tie-breaks / i32 counts", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "scans_per_step_per_gpu": B, "n_points": N_POINTS, "n_traversals": N_TRAV,
                    "ransac": "device-drawn minimal sets, 100 trials scored, sklearn accept/early-stop replay",
                    "l2": f"inputs larger than L2: {h2d_bytes / 1e6:.0f} MB touched per step",
