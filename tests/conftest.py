@@ -14,6 +14,11 @@ from helpers_modest import GOLDEN_CASES, GOLDEN_DIR, build_case, load_golden  # 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the shared library is a build artefact (git-ignored): build it when a fresh tree has none
+    lib = os.path.join(ROOT, "modest_b200", "libmodest_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.run(["bash", os.path.join(ROOT, "modest_b200", "csrc", "build.sh")], check=True)
 
 
 _case_cache = {}
