@@ -30,6 +30,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_POINTS, N_TRAV = 60000, 16
+# dram__bytes_read.sum + dram__bytes_write.sum of one pp_count_kernel launch of the default batch
+# (24 scans), from the `ncu --set full` capture summarised in
+# profiles/r1_final_pp_count_bench_launch_ncu_full_summary.csv (425.8 MB read + 69.3 MB written)
+PP_COUNT_DRAM_TRAFFIC_24_SCANS = 425_807_616 + 69_270_272
 METRIC = "LiDAR scans/sec (PP-score+RANSAC+DBSCAN+NMS) @60k pts"
 WORKLOAD = "full seed-label pipeline, synthetic Lyft-shape scans (60k pts, 16 traversals x 1 frame)"
 
@@ -280,7 +284,9 @@ def run_ours(args):
                 "h2d_gbs_used": round(h2d_bytes * args.steps / e2e_s / 1e9, 1)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "pp_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": PP_COUNT_DRAM_TRAFFIC_24_SCANS if B == 24 else None,
+                     "traffic_source": "ncu --set full, profiles/r1_final_pp_count_bench_launch_ncu_full_summary.csv",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": pp_ms,
                      "share_of_step": pp_ms / (ms / args.steps)},
     }
