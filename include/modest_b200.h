@@ -243,7 +243,6 @@ int modest_filter_and_fit_batch(const float* d_ptc, int point_stride, const int6
  *   q_f32   percentile/100 evaluated in float32 by the caller
  *   d_percentile (S,max_boxes) f32 out, d_count (S,max_boxes) i32 out (0 -> box holds no point)
  * Rect coordinates come from d_rect_in when given, else from d_ptc + d_calib.
- * Synchronises `stream` once (uploads a small offset table).
  * ------------------------------------------------------------------------------------------ */
 size_t modest_box_pp_workspace_bytes(int n_scans, int64_t n_points_total, int64_t max_points,
                                      int max_boxes);

@@ -616,8 +616,8 @@ __global__ void __launch_bounds__(256) box_pp_percentile_kernel(
     const int64_t* __restrict__ off, const double* __restrict__ rect, const float* __restrict__ pp,
     const double* __restrict__ boxes /* (S,max_boxes,8) t.x t.y t.z l w h ry _ */, const int32_t* __restrict__ n_boxes,
     const double* __restrict__ box_trig /* (S,max_boxes,2) cos(ry), sin(ry) from the host libm, or NULL */,
-    int max_boxes, float q, float* __restrict__ vals /* (S,max_boxes) slices of N_s floats */,
-    const int64_t* __restrict__ vals_off /* (S) */, float* __restrict__ pct_out, int32_t* __restrict__ cnt_out) {
+    int max_boxes, float q, float* __restrict__ vals /* (S,max_boxes) slices of max_points floats */,
+    int64_t max_points, float* __restrict__ pct_out, int32_t* __restrict__ cnt_out) {
   const int s = blockIdx.y, k = blockIdx.x;
   if (k >= n_boxes[s]) return;
   const int64_t beg = off[s];
@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(256) box_pp_percentile_kernel(
   const double c = box_trig ? box_trig[((size_t)s * max_boxes + k) * 2] : cos(ry);
   const double sn = box_trig ? box_trig[((size_t)s * max_boxes + k) * 2 + 1] : sin(ry);
   const double hl = __ddiv_rn(l, 2.0), hw = __ddiv_rn(w, 2.0), ylo = __dsub_rn(ty, h);
-  float* mine = vals + vals_off[s] + (size_t)k * n;
+  float* mine = vals + ((size_t)s * max_boxes + k) * (size_t)max_points;
   __shared__ int s_cnt;
   __shared__ unsigned hist[256];
   __shared__ unsigned sel[2];
@@ -719,6 +719,7 @@ extern "C" int modest_filter_and_fit_batch(
   float* beta32 = ar.take<float>((size_t)n_scans * max_valid * kMaxAngles);
   int32_t* valid_list = ar.take<int32_t>((size_t)n_scans * max_valid);
   float2* xz32 = ar.take<float2>(n_points_total);
+  MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
   int32_t* has_noise = nv_hn + n_scans;
 
   FilterCfg fc;
@@ -784,8 +785,7 @@ extern "C" int modest_filter_and_fit_batch(
 
 extern "C" size_t modest_box_pp_workspace_bytes(int n_scans, int64_t n_points_total, int64_t max_points, int max_boxes) {
   return align_up(sizeof(double) * 3 * (size_t)n_points_total, 256) + align_up(sizeof(CalibDev) * (size_t)n_scans, 256) +
-         align_up(sizeof(float) * (size_t)n_scans * max_boxes * (size_t)max_points, 256) +
-         align_up(sizeof(int64_t) * (size_t)n_scans, 256) + 1024;
+         align_up(sizeof(float) * (size_t)n_scans * max_boxes * (size_t)max_points, 256) + 1024;
 }
 
 extern "C" int modest_box_pp_percentile_batch(const float* d_ptc, int point_stride, const int64_t* d_off, const float* d_pp,
@@ -804,7 +804,7 @@ extern "C" int modest_box_pp_percentile_batch(const float* d_ptc, int point_stri
   double* rect_ws = ar.take<double>(3 * (size_t)n_points_total);
   CalibDev* calibs = ar.take<CalibDev>(n_scans);
   float* vals = ar.take<float>((size_t)n_scans * max_boxes * (size_t)max_points);
-  int64_t* vals_off = ar.take<int64_t>(n_scans);
+  MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
   const double* rect = d_rect_in ? d_rect_in : rect_ws;
   int pblocks = (int)((max_points + 255) / 256);
   if (pblocks < 1) pblocks = 1;
@@ -813,15 +813,8 @@ extern "C" int modest_box_pp_percentile_batch(const float* d_ptc, int point_stri
     rect_coords_kernel<<<dim3(pblocks, n_scans), 256, 0, stream>>>(d_ptc, point_stride, d_off, calibs, rect_ws);
     MODEST_LAUNCH_CHECK("rect_coords_kernel");
   }
-  // slice s starts at s * max_boxes * max_points (host-computed, uploaded once per call)
-  {
-    static thread_local int64_t h_off[65536];
-    for (int s = 0; s < n_scans; ++s) h_off[s] = (int64_t)s * max_boxes * max_points;
-    MODEST_CUDA(cudaMemcpyAsync(vals_off, h_off, sizeof(int64_t) * (size_t)n_scans, cudaMemcpyHostToDevice, stream));
-    MODEST_CUDA(cudaStreamSynchronize(stream));      // h_off is reused by the next call
-  }
   box_pp_percentile_kernel<<<dim3(max_boxes, n_scans), 256, 0, stream>>>(d_off, rect, d_pp, d_boxes, d_n_boxes, d_box_trig, max_boxes,
-                                                                        (float)q_f32, vals, vals_off, d_percentile, d_count);
+                                                                        (float)q_f32, vals, max_points, d_percentile, d_count);
   MODEST_LAUNCH_CHECK("box_pp_percentile_kernel");
   note_launch(d_rect_in ? 1 : 2);
   return MODEST_OK;

@@ -698,6 +698,7 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
   double* rk2 = ar.take<double>(n_points_total);
   int32_t* knn = ar.take<int32_t>((size_t)n_points_total * n_neighbors);
   int32_t* knn_cnt = ar.take<int32_t>(n_points_total);
+  MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
 
   const float cell = kGraphCell * kGraphSlack;
   int rc = grid2d_build(d_kept, 4, d_off, d_n_kept, n_scans, max_points, cell, G, meta, cells, sorted, stream);
@@ -754,6 +755,7 @@ extern "C" int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept
   uint8_t* core = ar.take<uint8_t>(n_points_total);
   int32_t* parent = ar.take<int32_t>(n_points_total);
   int32_t* root_rank = ar.take<int32_t>(n_points_total);
+  MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
   int32_t* border_lab = root_rank;
   int pblocks = (int)((max_points + 255) / 256);
   if (pblocks < 1) pblocks = 1;

@@ -292,6 +292,7 @@ static int nms_impl(const float* d_boxes, int n, float thr, long long* d_keep, l
   unsigned long long* removed = ar.take<unsigned long long>(blocks);
   long long* keep_ws = ar.take<long long>(n);
   int* num_dev = reinterpret_cast<int*>(ar.take<long long>(1));
+  MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
   long long* keep = d_keep ? d_keep : keep_ws;
   nms_mask_kernel<<<dim3(blocks, blocks), 64, 0, stream>>>(n, thr, d_boxes, mask, rotated);
   MODEST_LAUNCH_CHECK("nms_mask_kernel");

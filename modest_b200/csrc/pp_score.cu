@@ -582,6 +582,7 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
   float4* sorted = ar.take<float4>(n_query_total);
   int* counts = ar.take<int>(n_count_total);
   int32_t* trav_scan = ar.take<int32_t>(kMaxTraversals);
+  MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
 
   const float cell = (float)radius * kCellSlack;
   const double r2 = radius * radius;

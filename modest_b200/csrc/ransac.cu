@@ -393,6 +393,7 @@ extern "C" int modest_ransac_fit_batch(const float* d_cand, const int64_t* d_off
   Arena ar(d_ws, ws_bytes);
   Hyp* hyps = ar.take<Hyp>((size_t)n_scans * max_trials);
   HypStat* stats = ar.take<HypStat>((size_t)n_scans * max_trials);
+  MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
   MODEST_CUDA(cudaMemsetAsync(stats, 0, sizeof(HypStat) * (size_t)n_scans * max_trials, stream));
   ransac_hypotheses_kernel<<<n_scans, 128, 0, stream>>>(d_cand, d_off, d_n_cand, d_triples, seed, max_trials,
                                                         hyps, d_triples_out);

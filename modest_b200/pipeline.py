@@ -349,6 +349,24 @@ class SeedLabelPipeline:
         r.flags = dict(graph=gflags, fit=fflags)
         return r
 
+    @staticmethod
+    def check_flags(result: "BatchResult"):
+        """Raise when a fixed-capacity device buffer overflowed (results would be silently
+        truncated); warn about distance ties the reference resolves by traversal order."""
+        g = int(result.flags["graph"].item())
+        f = int(result.flags["fit"].item())
+        if f & 4:
+            raise RuntimeError("more DBSCAN clusters than max_clusters: rebuild the pipeline with a larger capacity")
+        if f & 16:
+            raise RuntimeError("more boxes than max_boxes: rebuild the pipeline with a larger capacity")
+        if g & 2:
+            raise RuntimeError("a point has more than n_neighbors equidistant k-th neighbours (duplicate points?)")
+        if f & 8:
+            raise ValueError("a fitted box contains no scan point (the reference raises on ys.max() of an empty array)")
+        if g & 1:
+            import warnings
+            warnings.warn("kNN distance ties: neighbour sets may differ from scikit-learn's traversal order")
+
     # ------------------------------------------------------------------ stage O (host)
     def label_texts(self, b: ScanBatch, boxes, n_boxes, keep):
         """KITTI label text per scan (gen_label_files.py:46-52); one D2H copy of the small box
