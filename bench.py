@@ -30,10 +30,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_POINTS, N_TRAV = 60000, 16
-# dram__bytes_read.sum + dram__bytes_write.sum of one pp_count_kernel launch of the default batch
-# (24 scans), from the `ncu --set full` capture summarised in
-# profiles/r1_final_pp_count_bench_launch_ncu_full_summary.csv (425.8 MB read + 69.3 MB written)
-PP_COUNT_DRAM_TRAFFIC_24_SCANS = 425_807_616 + 69_270_272
+# dram__bytes_read.sum + dram__bytes_write.sum of one pp_count_kernel launch over 24 scans, from the
+# `ncu --set full` capture summarised in profiles/r1_final_pp_count_bench_launch_ncu_full_summary.csv
+# (425.8 MB read + 69.3 MB written); the kernel's traffic is proportional to the scans per launch
+PP_COUNT_DRAM_TRAFFIC_PER_SCAN = (425_807_616 + 69_270_272) / 24
 METRIC = "LiDAR scans/sec (PP-score+RANSAC+DBSCAN+NMS) @60k pts"
 WORKLOAD = "full seed-label pipeline, synthetic Lyft-shape scans (60k pts, 16 traversals x 1 frame)"
 
@@ -284,8 +284,9 @@ def run_ours(args):
                 "h2d_gbs_used": round(h2d_bytes * args.steps / e2e_s / 1e9, 1)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "pp_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": PP_COUNT_DRAM_TRAFFIC_24_SCANS if B == 24 else None,
-                     "traffic_source": "ncu --set full, profiles/r1_final_pp_count_bench_launch_ncu_full_summary.csv",
+                     "frac": achieved / peak, "traffic": int(PP_COUNT_DRAM_TRAFFIC_PER_SCAN * B),
+                     "traffic_source": "ncu --set full of a 24-scan launch (profiles/r1_final_pp_count_bench_launch_ncu_full_summary.csv), "
+                                       "scaled to this launch's scan count",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": pp_ms,
                      "share_of_step": pp_ms / (ms / args.steps)},
@@ -308,7 +309,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scans-per-step", type=int, default=24)
+    ap.add_argument("--scans-per-step", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=2, help="independent pipeline lanes for the device-resident loop")
     args = ap.parse_args()
