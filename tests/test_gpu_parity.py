@@ -427,3 +427,49 @@ def test_combine_labels_merge(golden_case, name, tmp_path):
                    save_path=str(tmp_path / "out"), with_score=True, image_shape=list(shape.image_shape))
     cb.main(cfg)
     assert (tmp_path / "out" / f"{idx:06d}.txt").read_text() == str(g["merge_text"])
+
+
+def test_full_size_properties_lyft_shape():
+    """BASELINE.json full size (60k points, 16 traversals): size-independent properties instead of
+    an element-wise oracle run -- pair-count symmetry, permutation invariance, entropy bounds,
+    plus an oracle spot check on a random subset of query points."""
+    from oracle import modest_oracle as orc
+    from modest_b200 import synth
+    case = synth.make_scan_case(4242, synth.LYFT, n_traversals=16)
+    q, hist = case.query_fixed, case.history
+    pp, counts = pp_score.count_neighbors_and_score(q, hist, return_counts=True)
+    assert counts.shape == (60000, 16) and counts.min() >= 0
+    # symmetry: #{(q,h): |q-h| <= r} is the same with the roles of query and traversal swapped
+    for t in (0, 7, 15):
+        _, swapped = pp_score.count_neighbors_and_score(hist[t], [q, hist[(t + 1) % 16]], return_counts=True)
+        assert int(swapped[:, 0].sum()) == int(counts[:, t].sum())
+    # permutation invariance (history order is irrelevant; query order permutes the rows)
+    rng = np.random.default_rng(0)
+    perm_h = [h[rng.permutation(len(h))] for h in hist]
+    perm_q = rng.permutation(len(q))
+    pp2, counts2 = pp_score.count_neighbors_and_score(q[perm_q], perm_h, return_counts=True)
+    assert np.array_equal(counts2, counts[perm_q]) and np.array_equal(pp2, pp[perm_q])
+    # entropy: 0 <= H <= 1 (+rounding), exactly 0 for untouched points, ~1 for uniform rows
+    assert pp.min() >= -1e-6 and pp.max() <= 1 + 1e-6
+    assert np.all(pp[counts.sum(axis=1) == 0] == 0)
+    uniform = (counts.min(axis=1) == counts.max(axis=1)) & (counts.min(axis=1) > 0)
+    if uniform.any():
+        assert np.allclose(pp[uniform], 1.0, atol=1e-6)
+    # oracle spot check (cKDTree on 2 000 random query points, all 16 traversals)
+    sub = rng.choice(len(q), 2000, replace=False)
+    assert np.array_equal(counts[sub], orc.neighbor_counts(q[sub], hist))
+    # full pipeline at full size: labels are compact ids, boxes pass the gates, NMS is idempotent
+    p = pl.SeedLabelPipeline()
+    b = _batch(case, pp)
+    r = p.run(b, rng="device", seed=9)
+    p.check_flags(r)
+    lab = r.labels.cpu().numpy()
+    nb = int(r.n_boxes.cpu()[0])
+    assert lab.min() == 0 and lab.max() == nb and len(np.unique(lab)) == nb + 1
+    boxes = r.boxes.cpu().numpy()[0, :nb]
+    assert np.all((boxes[:, 7] > 0.5) & (boxes[:, 7] < 120)) and np.all(boxes[:, 3] >= boxes[:, 4] - 1e-9)
+    keep = r.keep.cpu().numpy()[0, :nb].astype(bool)
+    kept = torch.zeros((1, p.max_boxes, 8), dtype=torch.float64, device="cuda")
+    kept[0, :keep.sum()] = r.boxes[0, :nb][torch.from_numpy(keep).cuda()]
+    keep2, _ = p.seed_nms(kept, torch.tensor([int(keep.sum())], dtype=torch.int32, device="cuda"))
+    assert keep2.cpu().numpy()[0, :keep.sum()].all()
