@@ -137,6 +137,26 @@ int modest_ransac_fit_batch(const float* d_cand, const int64_t* d_off, const int
                             size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * road-plane files for OpenPCDet's ground-truth sampling.
+ * Replaces the numeric part of extract_ransac() (data_preprocessing/RANSAC.py:9-68): rect-camera
+ * coordinates in f64, candidates min_h < y < max_h, -10 < z < 70, -20 < x < 20 (in order),
+ * sklearn RANSACRegressor().fit((x,z), y) in float64, plane [a, -1, b, c] / |(a,-1,b)|; fewer than
+ * 5 candidates give the script's default [0, -1, 0, 1.65].  Same two-step protocol as stage E:
+ *   modest_road_candidates_batch: d_calib (S,21) f64 as for the box stage; d_cand (NP,3) f64 out,
+ *       rows (x, z, y) packed at d_off[s]; d_n_cand (S) i32 out; d_thr (S) f64 out (MAD of y)
+ *   modest_road_plane_fit_batch:  d_triples (S,max_trials,3) i32 or NULL (device draws);
+ *       d_plane (S,4) f64 out; d_info (S,4) i32 out; workspace as modest_ransac_workspace_bytes
+ * ------------------------------------------------------------------------------------------ */
+int modest_road_candidates_batch(const float* d_ptc, int point_stride, const int64_t* d_off,
+                                 const double* d_calib, int n_scans, double min_h, double max_h,
+                                 double* d_cand, int32_t* d_n_cand, double* d_thr, void* stream);
+int modest_road_plane_fit_batch(const double* d_cand, const int64_t* d_off,
+                                const int32_t* d_n_cand, const double* d_thr, int n_scans,
+                                int64_t max_points, const int32_t* d_triples, uint64_t seed,
+                                int max_trials, double* d_plane, int32_t* d_info, void* d_ws,
+                                size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stages F+G: ground removal and range gate, compacted.
  * Replaces above_plane()/distance_to_plane() (utils/pointcloud_utils.py:68-81) and the
  * limit_range product of generate_mask.py:57-65.  A point survives iff

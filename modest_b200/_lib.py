@@ -38,6 +38,9 @@ SIGNATURES = {
     "modest_ransac_workspace_bytes": (_sz, [C.c_int, C.c_int]),
     "modest_ransac_fit_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _i64, _vp, C.c_uint64, C.c_int,
                                           _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "modest_road_candidates_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _f64, _f64, _vp, _vp, _vp, _vp]),
+    "modest_road_plane_fit_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _i64, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp,
+                                              _sz, _vp]),
     "modest_ground_mask_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_int, _f64, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _vp]),
     "modest_graph_workspace_bytes": (_sz, [C.c_int, _i64, C.c_int, C.c_int]),

@@ -22,17 +22,37 @@
 namespace modest {
 extern void note_launch(int n);
 
-// ---- block-wide k-th smallest of f32 values (k 0-based), 1024 threads ------------------------
-template <typename F>
-__device__ float block_kth_smallest(int n, int k, F value, unsigned* hist /*[256] smem*/, unsigned* sel /*[2] smem*/) {
-  unsigned prefix = 0, mask = 0;
+// ---- scalar-type traits: float for the seed-mask planes, double for the road planes ------------
+template <typename T> struct Ord;
+template <> struct Ord<float> {
+  using U = unsigned;
+  static __device__ __forceinline__ U enc(float v) { return f32_ordered(v); }
+  static __device__ __forceinline__ float dec(U u) { return f32_from_ordered(u); }
+};
+template <> struct Ord<double> {
+  using U = unsigned long long;
+  static __device__ __forceinline__ U enc(double v) { return f64_ordered(v); }
+  static __device__ __forceinline__ double dec(U u) { return f64_from_ordered(u); }
+};
+__device__ __forceinline__ float t_abs(float v) { return fabsf(v); }
+__device__ __forceinline__ double t_abs(double v) { return fabs(v); }
+__device__ __forceinline__ float t_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double t_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float t_mean2(float a, float b) { return __fmul_rn(__fadd_rn(a, b), 0.5f); }
+__device__ __forceinline__ double t_mean2(double a, double b) { return __dmul_rn(__dadd_rn(a, b), 0.5); }
+
+// ---- block-wide k-th smallest of T values (k 0-based), 1024 threads ----------------------------
+template <typename T, typename F>
+__device__ T block_kth_smallest(int n, int k, F value, unsigned* hist /*[256] smem*/, unsigned* sel /*[2] smem*/) {
+  using U = typename Ord<T>::U;
+  U prefix = 0, mask = 0;
   int kk = k;
-  for (int shift = 24; shift >= 0; shift -= 8) {
+  for (int shift = 8 * (int)sizeof(T) - 8; shift >= 0; shift -= 8) {
     for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      unsigned u = f32_ordered(value(i));
-      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+      const U u = Ord<T>::enc(value(i));
+      if ((u & mask) == prefix) atomicAdd(&hist[(unsigned)(u >> shift) & 255u], 1u);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -46,22 +66,22 @@ __device__ float block_kth_smallest(int n, int k, F value, unsigned* hist /*[256
       sel[1] = acc;
     }
     __syncthreads();
-    prefix |= sel[0] << shift;
-    mask |= 255u << shift;
+    prefix |= (U)sel[0] << shift;
+    mask |= (U)255u << shift;
     kk -= (int)sel[1];
     __syncthreads();
   }
-  return f32_from_ordered(prefix);
+  return Ord<T>::dec(prefix);
 }
 
-// numpy.median of a float32 vector: middle element, or the f32 mean of the two middle ones.
-template <typename F>
-__device__ float block_median_f32(int n, F value, unsigned* hist, unsigned* sel) {
-  if (n <= 0) return 0.f;
-  const float hi = block_kth_smallest(n, n / 2, value, hist, sel);
+// numpy.median: middle element, or the mean (in T) of the two middle ones.
+template <typename T, typename F>
+__device__ T block_median(int n, F value, unsigned* hist, unsigned* sel) {
+  if (n <= 0) return (T)0;
+  const T hi = block_kth_smallest<T>(n, n / 2, value, hist, sel);
   if (n & 1) return hi;
-  const float lo = block_kth_smallest(n, n / 2 - 1, value, hist, sel);
-  return __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+  const T lo = block_kth_smallest<T>(n, n / 2 - 1, value, hist, sel);
+  return t_mean2(lo, hi);
 }
 
 // ---- 1. ordered compaction of plane candidates -------------------------------------------------
@@ -110,21 +130,22 @@ __global__ void __launch_bounds__(1024) plane_candidates_kernel(
 }
 
 // ---- 2. MAD threshold ---------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(1024) mad_threshold_kernel(
-    const float* __restrict__ cand, const int64_t* __restrict__ off, const int32_t* __restrict__ n_cand,
-    float* __restrict__ thr) {
+    const T* __restrict__ cand, const int64_t* __restrict__ off, const int32_t* __restrict__ n_cand,
+    T* __restrict__ thr) {
   const int s = blockIdx.x;
-  const float* z = cand + 3 * off[s] + 2;
+  const T* z = cand + 3 * off[s] + 2;
   const int n = n_cand[s];
   __shared__ unsigned hist[256];
   __shared__ unsigned sel[2];
-  const float med = block_median_f32(n, [&](int i) { return z[3 * i]; }, hist, sel);
-  const float mad = block_median_f32(n, [&](int i) { return fabsf(__fsub_rn(z[3 * i], med)); }, hist, sel);
+  const T med = block_median<T>(n, [&](int i) { return z[3 * i]; }, hist, sel);
+  const T mad = block_median<T>(n, [&](int i) { return t_abs(t_sub(z[3 * i], med)); }, hist, sel);
   if (threadIdx.x == 0) thr[s] = mad;
 }
 
 // ---- 3. hypotheses ------------------------------------------------------------------------------
-struct Hyp { float a, b, c; int valid; };
+template <typename T> struct HypT { T a, b, c; int valid; int pad; };
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
@@ -133,15 +154,16 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
+template <typename T>
 __global__ void ransac_hypotheses_kernel(
-    const float* __restrict__ cand, const int64_t* __restrict__ off, const int32_t* __restrict__ n_cand,
-    const int32_t* __restrict__ triples, uint64_t seed, int H, Hyp* __restrict__ hyps,
+    const T* __restrict__ cand, const int64_t* __restrict__ off, const int32_t* __restrict__ n_cand,
+    const int32_t* __restrict__ triples, uint64_t seed, int H, HypT<T>* __restrict__ hyps,
     int32_t* __restrict__ triples_out) {
   const int s = blockIdx.x;
   const int n = n_cand[s];
-  const float* p = cand + 3 * off[s];
+  const T* p = cand + 3 * off[s];
   for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    Hyp out = {0.f, 0.f, 0.f, 0};
+    HypT<T> out = {(T)0, (T)0, (T)0, 0, 0};
     int id[3] = {0, 0, 0};
     bool ok = n >= 3;
     if (ok) {
@@ -174,8 +196,8 @@ __global__ void ransac_hypotheses_kernel(
       const double det = sxx * syy - sxy * sxy;
       if (fabs(det) > 1e-30 * (sxx * syy + 1e-300)) {
         const double a = (sxz * syy - syz * sxy) / det, b = (syz * sxx - sxz * sxy) / det;
-        out.a = (float)a; out.b = (float)b;
-        out.c = (float)(mz - a * mx - b * my);
+        out.a = (T)a; out.b = (T)b;
+        out.c = (T)(mz - a * mx - b * my);
         out.valid = 1;
       }
     }
@@ -189,43 +211,49 @@ struct HypStat { int count; int pad; double ss_res, sum_z, sum_zz; };
 
 constexpr int kPtsPerThread = 8;
 
-__device__ __forceinline__ float predict_f32(const Hyp& h, float x, float y) {
-  // float32 model evaluation: (x*a + y*b) + c  (numpy's f32 matmul then the intercept add)
+// model evaluation X @ coef + intercept exactly as numpy/OpenBLAS round it (measured on this
+// image, tests/test_host_logic.py): sgemv gives fma(y,b, x*a), dgemv gives fma(x,a, y*b)
+__device__ __forceinline__ float predict(const HypT<float>& h, float x, float y) {
   return __fadd_rn(fmaf(y, h.b, __fmul_rn(x, h.a)), h.c);
 }
+__device__ __forceinline__ double predict(const HypT<double>& h, double x, double y) {
+  return __dadd_rn(__fma_rn(x, h.a, __dmul_rn(y, h.b)), h.c);
+}
 
+template <typename T>
 __global__ void __launch_bounds__(256) ransac_score_kernel(
-    const float* __restrict__ cand, const int64_t* __restrict__ off, const int32_t* __restrict__ n_cand,
-    const float* __restrict__ thr, const Hyp* __restrict__ hyps, int H, HypStat* __restrict__ stats) {
+    const T* __restrict__ cand, const int64_t* __restrict__ off, const int32_t* __restrict__ n_cand,
+    const T* __restrict__ thr, const HypT<T>* __restrict__ hyps, int H, HypStat* __restrict__ stats) {
   const int s = blockIdx.y;
   const int n = n_cand[s];
   const int chunk = 256 * kPtsPerThread;
   const int start = blockIdx.x * chunk;
   if (start >= n) return;
-  extern __shared__ Hyp sh_h[];
+  extern __shared__ __align__(16) unsigned char sh_raw[];
+  HypT<T>* sh_h = reinterpret_cast<HypT<T>*>(sh_raw);
   for (int h = threadIdx.x; h < H; h += blockDim.x) sh_h[h] = hyps[(size_t)s * H + h];
   __syncthreads();
-  const float* p = cand + 3 * off[s];
-  const float t = thr[s];
-  float x[kPtsPerThread], y[kPtsPerThread], z[kPtsPerThread];
+  const T* p = cand + 3 * off[s];
+  const T t = thr[s];
+  T x[kPtsPerThread], y[kPtsPerThread], z[kPtsPerThread];
   bool live[kPtsPerThread];
 #pragma unroll
   for (int k = 0; k < kPtsPerThread; ++k) {
     const int i = start + k * 256 + threadIdx.x;
     live[k] = i < n;
-    x[k] = live[k] ? p[3 * i] : 0.f;
-    y[k] = live[k] ? p[3 * i + 1] : 0.f;
-    z[k] = live[k] ? p[3 * i + 2] : 0.f;
+    x[k] = live[k] ? p[3 * i] : (T)0;
+    y[k] = live[k] ? p[3 * i + 1] : (T)0;
+    z[k] = live[k] ? p[3 * i + 2] : (T)0;
   }
   const int lane = threadIdx.x & 31;
   for (int h = 0; h < H; ++h) {
-    const Hyp hy = sh_h[h];
+    const HypT<T> hy = sh_h[h];
     if (!hy.valid) continue;
     int cnt = 0;
     double ssr = 0.0, sz = 0.0, szz = 0.0;
 #pragma unroll
     for (int k = 0; k < kPtsPerThread; ++k) {
-      const float r = fabsf(__fsub_rn(z[k], predict_f32(hy, x[k], y[k])));
+      const T r = t_abs(t_sub(z[k], predict(hy, x[k], y[k])));
       if (live[k] && r <= t) {
         ++cnt;
         const double rd = (double)r, zd = (double)z[k];
@@ -256,7 +284,8 @@ __device__ double dynamic_max_trials(int n_inliers, int n_samples) {
   return fabs(ceil(log(nom) / log(denom)));
 }
 
-__global__ void ransac_select_kernel(const HypStat* __restrict__ stats, const Hyp* __restrict__ hyps,
+template <typename T>
+__global__ void ransac_select_kernel(const HypStat* __restrict__ stats, const HypT<T>* __restrict__ hyps,
                                      const int32_t* __restrict__ n_cand, int H, int n_scans,
                                      int32_t* __restrict__ info /* (S,4): n_cand, n_trials, best, best_inliers */) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,26 +328,34 @@ __device__ double block_sum(double v, double* sh /*[32]*/) {
   return r;
 }
 
+// mode 0: seed-mask plane of utils/pointcloud_utils.py:53-62  -> -[a, b, -1, c]/|(a,b,-1)|  (c > 0)
+// mode 1: road plane of data_preprocessing/RANSAC.py:44-52    ->  [a, -1, b, c]/|(a,-1,b)|   (features are
+//         rect x and z, target rect y); fewer than 5 candidates -> the script's default [0,-1,0,1.65]
+template <typename T>
 __global__ void __launch_bounds__(1024) ransac_refit_kernel(
-    const float* __restrict__ cand, const int64_t* __restrict__ off, const int32_t* __restrict__ n_cand,
-    const float* __restrict__ thr, const Hyp* __restrict__ hyps, int H, const int32_t* __restrict__ info,
+    const T* __restrict__ cand, const int64_t* __restrict__ off, const int32_t* __restrict__ n_cand,
+    const T* __restrict__ thr, const HypT<T>* __restrict__ hyps, int H, const int32_t* __restrict__ info,
     double* __restrict__ plane /* (S,4) */, double* __restrict__ model /* (S,3) a,b,c or NULL */,
-    uint8_t* __restrict__ inlier_mask /* per candidate, at off[s], or NULL */) {
+    uint8_t* __restrict__ inlier_mask /* per candidate, at off[s], or NULL */, int mode) {
   const int s = blockIdx.x;
   const int n = n_cand[s];
   const int best = info[4 * s + 2];
-  const float* p = cand + 3 * off[s];
+  const T* p = cand + 3 * off[s];
   __shared__ double sh[32];
+  if (mode == 1 && n < 5) {
+    if (threadIdx.x == 0) { plane[4 * s] = 0.0; plane[4 * s + 1] = -1.0; plane[4 * s + 2] = 0.0; plane[4 * s + 3] = 1.65; }
+    return;
+  }
   if (best < 0) {
     if (threadIdx.x < 4) plane[4 * s + threadIdx.x] = __longlong_as_double(0x7ff8000000000000ll);
     return;
   }
-  const Hyp hy = hyps[(size_t)s * H + best];
-  const float t = thr[s];
+  const HypT<T> hy = hyps[(size_t)s * H + best];
+  const T t = thr[s];
   double cnt = 0, sx = 0, sy = 0, sz = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
-    const bool in = fabsf(__fsub_rn(z, predict_f32(hy, x, y))) <= t;
+    const T x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+    const bool in = t_abs(t_sub(z, predict(hy, x, y))) <= t;
     if (inlier_mask) inlier_mask[off[s] + i] = in ? 1 : 0;
     if (in) { cnt += 1.0; sx += x; sy += y; sz += z; }
   }
@@ -326,8 +363,8 @@ __global__ void __launch_bounds__(1024) ransac_refit_kernel(
   const double mx = sx / cnt, my = sy / cnt, mz = sz / cnt;
   double sxx = 0, sxy = 0, syy = 0, sxz = 0, syz = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
-    if (fabsf(__fsub_rn(z, predict_f32(hy, x, y))) <= t) {
+    const T x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+    if (t_abs(t_sub(z, predict(hy, x, y))) <= t) {
       const double dx = x - mx, dy = y - my, dz = z - mz;
       sxx += dx * dx; sxy += dx * dy; syy += dy * dy; sxz += dx * dz; syz += dy * dz;
     }
@@ -336,19 +373,109 @@ __global__ void __launch_bounds__(1024) ransac_refit_kernel(
   sxz = block_sum(sxz, sh); syz = block_sum(syz, sh);
   if (threadIdx.x == 0) {
     const double det = sxx * syy - sxy * sxy;
-    double a = (sxz * syy - syz * sxy) / det, b = (syz * sxx - sxz * sxy) / det;
-    // sklearn keeps coef_/intercept_ in the input dtype (float32)
-    const float af = (float)a, bf = (float)b;
-    const float cf = (float)(mz - a * mx - b * my);
+    const double a = (sxz * syy - syz * sxy) / det, b = (syz * sxx - sxz * sxy) / det;
+    // sklearn keeps coef_/intercept_ in the input dtype
+    const T af = (T)a, bf = (T)b;
+    const T cf = (T)(mz - a * mx - b * my);
     if (model) { model[3 * s] = af; model[3 * s + 1] = bf; model[3 * s + 2] = cf; }
-    // utils/pointcloud_utils.py:53-62: w = (a, b, -1)/|w|, h/|w|, all negated
-    const double wa = af, wb = bf, wc = -1.0;
-    const double nrm = sqrt(wa * wa + wb * wb + wc * wc);
-    plane[4 * s + 0] = -(wa / nrm);
-    plane[4 * s + 1] = -(wb / nrm);
-    plane[4 * s + 2] = -(wc / nrm);
-    plane[4 * s + 3] = -((double)cf / nrm);
+    const double wa = af, wb = bf;
+    const double nrm = sqrt(wa * wa + wb * wb + 1.0);
+    if (mode == 0) {
+      plane[4 * s + 0] = -(wa / nrm);
+      plane[4 * s + 1] = -(wb / nrm);
+      plane[4 * s + 2] = -(-1.0 / nrm);
+      plane[4 * s + 3] = -((double)cf / nrm);
+    } else {
+      plane[4 * s + 0] = wa / nrm;
+      plane[4 * s + 1] = -1.0 / nrm;
+      plane[4 * s + 2] = wb / nrm;
+      plane[4 * s + 3] = (double)cf / nrm;
+    }
   }
+}
+
+// road-plane candidates (data_preprocessing/RANSAC.py:31-37): rect coordinates in f64, keep
+// min_h < y < max_h, -10 < z < 70, -20 < x < 20 in order; candidate rows are (x, z, y)
+struct RoadCalib { double v2c[12]; double r0[9]; };
+
+__global__ void __launch_bounds__(1024) road_candidates_kernel(
+    const float* __restrict__ ptc, int stride, const int64_t* __restrict__ off, const RoadCalib* __restrict__ calibs,
+    double min_h, double max_h, double* __restrict__ cand, int32_t* __restrict__ n_cand) {
+  const int s = blockIdx.x;
+  const int64_t beg = off[s];
+  const int n = (int)(off[s + 1] - beg);
+  const RoadCalib cb = calibs[s];
+  double* out = cand + 3 * beg;
+  __shared__ int warp_cnt[32];
+  __shared__ int tile_total;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int base = 0;
+  for (int t0 = 0; t0 < n; t0 += 1024) {
+    const int i = t0 + threadIdx.x;
+    double r[3] = {0, 0, 0};
+    bool keep = false;
+    if (i < n) {
+      const float* p = ptc + (size_t)stride * (beg + i);
+      double ref[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)      // [p,1] @ V2C^T then R0 @ ref, dgemm's k-ordered fused multiply-adds
+        ref[k] = __fma_rn(1.0, cb.v2c[4 * k + 3], __fma_rn((double)p[2], cb.v2c[4 * k + 2],
+                          __fma_rn((double)p[1], cb.v2c[4 * k + 1], __dmul_rn((double)p[0], cb.v2c[4 * k]))));
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        r[k] = __fma_rn(cb.r0[3 * k + 2], ref[2], __fma_rn(cb.r0[3 * k + 1], ref[1], __dmul_rn(cb.r0[3 * k], ref[0])));
+      keep = (r[1] > min_h) && (r[1] < max_h) && (r[2] > -10.0) && (r[2] < 70.0) && (r[0] > -20.0) && (r[0] < 20.0);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[w] = __popc(bal);
+    __syncthreads();
+    if (w == 0) {
+      int c = warp_cnt[lane], inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      warp_cnt[lane] = inc - c;
+      if (lane == 31) tile_total = inc;
+    }
+    __syncthreads();
+    if (keep) {
+      const int pos = base + warp_cnt[w] + __popc(bal & ((1u << lane) - 1u));
+      out[3 * pos] = r[0]; out[3 * pos + 1] = r[2]; out[3 * pos + 2] = r[1];
+    }
+    base += tile_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) n_cand[s] = base;
+}
+
+template <typename T>
+static int ransac_fit_impl(const T* d_cand, const int64_t* d_off, const int32_t* d_n_cand, const T* d_thr, int n_scans,
+                           int64_t max_points, const int32_t* d_triples, uint64_t seed, int max_trials, double* d_plane,
+                           double* d_model, int32_t* d_info, int32_t* d_triples_out, uint8_t* d_inlier_mask, void* d_ws,
+                           size_t ws_bytes, cudaStream_t stream, int mode) {
+  Arena ar(d_ws, ws_bytes);
+  HypT<T>* hyps = ar.take<HypT<T>>((size_t)n_scans * max_trials);
+  HypStat* stats = ar.take<HypStat>((size_t)n_scans * max_trials);
+  MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
+  MODEST_CUDA(cudaMemsetAsync(stats, 0, sizeof(HypStat) * (size_t)n_scans * max_trials, stream));
+  ransac_hypotheses_kernel<T><<<n_scans, 128, 0, stream>>>(d_cand, d_off, d_n_cand, d_triples, seed, max_trials, hyps,
+                                                          d_triples_out);
+  MODEST_LAUNCH_CHECK("ransac_hypotheses_kernel");
+  const int chunk = 256 * kPtsPerThread;
+  dim3 grid((unsigned)((max_points + chunk - 1) / chunk), n_scans);
+  if (grid.x == 0) grid.x = 1;
+  ransac_score_kernel<T><<<grid, 256, sizeof(HypT<T>) * max_trials, stream>>>(d_cand, d_off, d_n_cand, d_thr, hyps,
+                                                                             max_trials, stats);
+  MODEST_LAUNCH_CHECK("ransac_score_kernel");
+  ransac_select_kernel<T><<<(n_scans + 63) / 64, 64, 0, stream>>>(stats, hyps, d_n_cand, max_trials, n_scans, d_info);
+  MODEST_LAUNCH_CHECK("ransac_select_kernel");
+  ransac_refit_kernel<T><<<n_scans, 1024, 0, stream>>>(d_cand, d_off, d_n_cand, d_thr, hyps, max_trials, d_info, d_plane,
+                                                     d_model, d_inlier_mask, mode);
+  MODEST_LAUNCH_CHECK("ransac_refit_kernel");
+  note_launch(4);
+  return MODEST_OK;
 }
 
 }  // namespace modest
@@ -366,15 +493,24 @@ extern "C" int modest_plane_candidates_batch(const float* d_ptc, int point_strid
   plane_candidates_kernel<<<n_scans, 1024, 0, stream>>>(d_ptc, point_stride, d_off, max_hs, x_lo, x_hi, y_lo,
                                                         y_hi, d_cand, d_n_cand);
   MODEST_LAUNCH_CHECK("plane_candidates_kernel");
-  mad_threshold_kernel<<<n_scans, 1024, 0, stream>>>(d_cand, d_off, d_n_cand, d_thr);
+  mad_threshold_kernel<float><<<n_scans, 1024, 0, stream>>>(d_cand, d_off, d_n_cand, d_thr);
   MODEST_LAUNCH_CHECK("mad_threshold_kernel");
   note_launch(2);
   return MODEST_OK;
 }
 
 extern "C" size_t modest_ransac_workspace_bytes(int n_scans, int max_trials) {
-  return align_up(sizeof(Hyp) * (size_t)n_scans * max_trials, 256) +
+  return align_up(sizeof(HypT<double>) * (size_t)n_scans * max_trials, 256) +
          align_up(sizeof(HypStat) * (size_t)n_scans * max_trials, 256) + 512;
+}
+
+static int fit_args_ok(const void* d_cand, const void* d_off, const void* d_n_cand, const void* d_thr, const void* d_plane,
+                       const void* d_info, const void* d_ws, int n_scans, int max_trials, size_t ws_bytes) {
+  MODEST_REQUIRE(d_cand && d_off && d_n_cand && d_thr && d_plane && d_info && d_ws, "ransac_fit: null pointer argument");
+  MODEST_REQUIRE(max_trials >= 1 && max_trials <= 1024, "ransac_fit: max_trials %d out of range", max_trials);
+  MODEST_REQUIRE(ws_bytes >= modest_ransac_workspace_bytes(n_scans, max_trials), "ransac_fit: workspace too small");
+  MODEST_REQUIRE(n_scans <= 65535, "ransac_fit: more than 65535 scans in one launch");
+  return MODEST_OK;
 }
 
 extern "C" int modest_ransac_fit_batch(const float* d_cand, const int64_t* d_off, const int32_t* d_n_cand,
@@ -383,32 +519,40 @@ extern "C" int modest_ransac_fit_batch(const float* d_cand, const int64_t* d_off
                                        double* d_plane, double* d_model, int32_t* d_info,
                                        int32_t* d_triples_out, uint8_t* d_inlier_mask, void* d_ws,
                                        size_t ws_bytes, void* stream_) {
+  if (n_scans <= 0) return MODEST_OK;
+  const int rc = fit_args_ok(d_cand, d_off, d_n_cand, d_thr, d_plane, d_info, d_ws, n_scans, max_trials, ws_bytes);
+  if (rc != MODEST_OK) return rc;
+  return ransac_fit_impl<float>(d_cand, d_off, d_n_cand, d_thr, n_scans, max_points, d_triples, seed, max_trials, d_plane,
+                                d_model, d_info, d_triples_out, d_inlier_mask, d_ws, ws_bytes,
+                                static_cast<cudaStream_t>(stream_), 0);
+}
+
+extern "C" int modest_road_candidates_batch(const float* d_ptc, int point_stride, const int64_t* d_off,
+                                            const double* d_calib, int n_scans, double min_h, double max_h,
+                                            double* d_cand, int32_t* d_n_cand, double* d_thr, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scans <= 0) return MODEST_OK;
-  MODEST_REQUIRE(d_cand && d_off && d_n_cand && d_thr && d_plane && d_info && d_ws,
-                 "ransac_fit: null pointer argument");
-  MODEST_REQUIRE(max_trials >= 1 && max_trials <= 1024, "ransac_fit: max_trials %d out of range", max_trials);
-  MODEST_REQUIRE(ws_bytes >= modest_ransac_workspace_bytes(n_scans, max_trials), "ransac_fit: workspace too small");
-  MODEST_REQUIRE(n_scans <= 65535, "ransac_fit: more than 65535 scans in one launch");
-  Arena ar(d_ws, ws_bytes);
-  Hyp* hyps = ar.take<Hyp>((size_t)n_scans * max_trials);
-  HypStat* stats = ar.take<HypStat>((size_t)n_scans * max_trials);
-  MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
-  MODEST_CUDA(cudaMemsetAsync(stats, 0, sizeof(HypStat) * (size_t)n_scans * max_trials, stream));
-  ransac_hypotheses_kernel<<<n_scans, 128, 0, stream>>>(d_cand, d_off, d_n_cand, d_triples, seed, max_trials,
-                                                        hyps, d_triples_out);
-  MODEST_LAUNCH_CHECK("ransac_hypotheses_kernel");
-  const int chunk = 256 * kPtsPerThread;
-  dim3 grid((unsigned)((max_points + chunk - 1) / chunk), n_scans);
-  if (grid.x == 0) grid.x = 1;
-  ransac_score_kernel<<<grid, 256, sizeof(Hyp) * max_trials, stream>>>(d_cand, d_off, d_n_cand, d_thr, hyps,
-                                                                      max_trials, stats);
-  MODEST_LAUNCH_CHECK("ransac_score_kernel");
-  ransac_select_kernel<<<(n_scans + 63) / 64, 64, 0, stream>>>(stats, hyps, d_n_cand, max_trials, n_scans, d_info);
-  MODEST_LAUNCH_CHECK("ransac_select_kernel");
-  ransac_refit_kernel<<<n_scans, 1024, 0, stream>>>(d_cand, d_off, d_n_cand, d_thr, hyps, max_trials, d_info,
-                                                    d_plane, d_model, d_inlier_mask);
-  MODEST_LAUNCH_CHECK("ransac_refit_kernel");
-  note_launch(4);
+  MODEST_REQUIRE(d_ptc && d_off && d_calib && d_cand && d_n_cand && d_thr, "road_candidates: null pointer argument");
+  MODEST_REQUIRE(point_stride >= 3, "road_candidates: point_stride %d < 3", point_stride);
+  road_candidates_kernel<<<n_scans, 1024, 0, stream>>>(d_ptc, point_stride, d_off,
+                                                       reinterpret_cast<const RoadCalib*>(d_calib), min_h, max_h, d_cand,
+                                                       d_n_cand);
+  MODEST_LAUNCH_CHECK("road_candidates_kernel");
+  mad_threshold_kernel<double><<<n_scans, 1024, 0, stream>>>(d_cand, d_off, d_n_cand, d_thr);
+  MODEST_LAUNCH_CHECK("mad_threshold_kernel");
+  note_launch(2);
   return MODEST_OK;
+}
+
+extern "C" int modest_road_plane_fit_batch(const double* d_cand, const int64_t* d_off, const int32_t* d_n_cand,
+                                           const double* d_thr, int n_scans, int64_t max_points,
+                                           const int32_t* d_triples, uint64_t seed, int max_trials,
+                                           double* d_plane, int32_t* d_info, void* d_ws, size_t ws_bytes,
+                                           void* stream_) {
+  if (n_scans <= 0) return MODEST_OK;
+  const int rc = fit_args_ok(d_cand, d_off, d_n_cand, d_thr, d_plane, d_info, d_ws, n_scans, max_trials, ws_bytes);
+  if (rc != MODEST_OK) return rc;
+  return ransac_fit_impl<double>(d_cand, d_off, d_n_cand, d_thr, n_scans, max_points, d_triples, seed, max_trials,
+                                 d_plane, nullptr, d_info, nullptr, nullptr, d_ws, ws_bytes,
+                                 static_cast<cudaStream_t>(stream_), 1);
 }

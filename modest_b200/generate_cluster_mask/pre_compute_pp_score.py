@@ -61,22 +61,30 @@ def display_args(args):
 
 
 class FrameStore:
-    """velodyne/*.bin frames as pinned host tensors, read once and reused across scans
-    (consecutive scans share most of their history frames)."""
+    """velodyne/*.bin frames, read once and kept where the next scan needs them: consecutive query
+    scans share most of their history frames (36 frames x T traversals per scan on
+    Lyft), so raw frames stay resident on the GPU in an LRU cache bounded by `device_bytes`."""
 
-    def __init__(self, root, capacity=512):
-        self.root, self.capacity, self._d = root, capacity, {}
+    def __init__(self, root, device_bytes=16 << 30):
+        self.root, self.device_bytes = root, int(device_bytes)
+        self._d, self._used = {}, 0
+        self.hits = self.misses = 0
 
     def get(self, fid):
-        t = self._d.get(fid)
-        if t is None:
-            arr = np.fromfile(osp.join(self.root, "velodyne", f"{fid:06d}.bin"), dtype=np.float32).reshape(-1, 4)
-            t = torch.from_numpy(arr)
-            if torch.cuda.is_available():
-                t = t.pin_memory()
-            if len(self._d) >= self.capacity:
-                self._d.pop(next(iter(self._d)))
-            self._d[fid] = t
+        t = self._d.pop(fid, None)
+        if t is not None:
+            self._d[fid] = t                       # most recently used goes last
+            self.hits += 1
+            return t
+        self.misses += 1
+        arr = np.fromfile(osp.join(self.root, "velodyne", f"{fid:06d}.bin"), dtype=np.float32).reshape(-1, 4)
+        t = torch.from_numpy(arr).cuda(non_blocking=False)
+        nbytes = t.numel() * 4
+        while self._d and self._used + nbytes > self.device_bytes:
+            oldest = next(iter(self._d))            # dicts keep insertion order: first = least recently used
+            self._used -= self._d.pop(oldest).numel() * 4
+        self._d[fid] = t
+        self._used += nbytes
         return t
 
 
@@ -84,7 +92,7 @@ def transform_frames(frames, mats, remove_center):
     """Upload raw (n,4) frames and bring them into the fixed frame with one kernel launch."""
     sizes = [int(f.shape[0]) for f in frames]
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    raw = torch.cat([f.cuda(non_blocking=True) for f in frames])
+    raw = torch.cat([f if f.is_cuda else f.cuda(non_blocking=True) for f in frames])
     T = torch.from_numpy(np.stack([np.asarray(m, np.float32).reshape(16) for m in mats])).cuda()
     out = torch.empty((raw.shape[0], 3), dtype=torch.float32, device="cuda")
     box = np.array([-1.15, 1.75, -0.65, 0.65], dtype=np.float32)      # pre_compute_pp_score.py:48

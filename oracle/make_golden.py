@@ -238,6 +238,34 @@ def main():
         o_text, _ = orc.merge_labels_for_scan(preds, copy.deepcopy(R["objs"]), rect_all, pp, orc.Calib(R["calib_path"]),
                                               lambda b: iou_m, image_shape=shape.image_shape, with_score=True)
         assert o_text == merge_text, "merge text restatement"
+        # ---------------- f-3: road plane via the reference's own script ----------------
+        import importlib.util
+        import io
+        import contextlib
+        dp_dir = os.path.join(rh.REFERENCE_ROOT, "data_preprocessing")
+        sys.path.insert(0, dp_dir)
+        try:
+            spec = importlib.util.spec_from_file_location("ref_road_ransac", os.path.join(dp_dir, "RANSAC.py"))
+            ref_road = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(ref_road)
+        finally:
+            sys.path.remove(dp_dir)
+            sys.modules.pop("kitti_util", None)
+        rd = tempfile.mkdtemp(prefix="modest_road_")
+        os.makedirs(os.path.join(rd, "calib")); os.makedirs(os.path.join(rd, "velodyne"))
+        synth.write_calib(os.path.join(rd, "calib", "000000.txt"), case.calib)
+        case.query.tofile(os.path.join(rd, "velodyne", "000000.bin"))
+        np.random.seed(77 + case.scan_id)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref_road.extract_ransac(os.path.join(rd, "calib"), os.path.join(rd, "velodyne"), os.path.join(rd, "planes"),
+                                    min_h=shape.sensor_height - 0.3, max_h=shape.sensor_height + 0.3)
+        road_text = open(os.path.join(rd, "planes", "000000.txt")).read()
+        np.random.seed(77 + case.scan_id)
+        ow, oh = orc.road_plane_for_scan(case.query, orc.Calib(R["calib_path"]), shape.sensor_height - 0.3,
+                                         shape.sensor_height + 0.3)
+        assert orc.road_plane_text(ow, oh) == road_text, "road plane restatement"
+        import shutil
+        shutil.rmtree(rd)
         g_sorted = g.copy()
         g_sorted.sort_indices()
         np.savez_compressed(
@@ -254,7 +282,7 @@ def main():
             calib_R0=np.asarray(case.calib["R0_rect"]), image_shape=np.array(shape.image_shape),
             max_hs=shape.max_hs, det_location=preds["location"], det_dimensions=preds["dimensions"],
             det_rotation_y=preds["rotation_y"], det_score=preds["score"], det_pp_gate=ref_gate,
-            merge_iou_cpu=iou_m, merge_text=merge_text)
+            merge_iou_cpu=iou_m, merge_text=merge_text, road_text=road_text, road_plane=np.array([*ow, oh]))
         meta["cases"][name] = dict(n_points=N, n_kept=int(R["final_mask"].sum()), graph_nnz=int(g.nnz),
                                    n_clusters_raw=int(R["labels_raw"].max() + 1), n_boxes=len(R["objs"]),
                                    n_labels=R["label_text"].count("\n") + (1 if R["label_text"] else 0),

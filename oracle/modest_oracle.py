@@ -650,6 +650,30 @@ def kitti_label_text(objs, calib, obj_type="Dynamic", with_score=False):
 
 
 # ------------------------------------------------------------------------------------------
+# f-3  road planes (data_preprocessing/RANSAC.py)
+# ------------------------------------------------------------------------------------------
+def road_plane_for_scan(pc_velo, calib, min_h=1.5, max_h=2.0):
+    """data_preprocessing/RANSAC.py:28-52 -- RANSAC on rect (x,z)->y of the points with
+    min_h < y < max_h, -10 < z < 70, -20 < x < 20; returns (w (3,), h) as written to the file."""
+    from sklearn.linear_model import RANSACRegressor
+    rect = calib.velo_to_rect(pc_velo[:, :3])
+    ok = ((rect[:, 1] > min_h) & (rect[:, 1] < max_h) & (rect[:, 2] > -10) & (rect[:, 2] < 70)
+          & (rect[:, 0] > -20) & (rect[:, 0] < 20))
+    rect = rect[ok]
+    if len(rect) < 5:
+        return np.array([0.0, -1.0, 0.0]), 1.65
+    reg = RANSACRegressor().fit(rect[:, [0, 2]], rect[:, 1])
+    w = np.array([reg.estimator_.coef_[0], -1.0, reg.estimator_.coef_[1]])
+    nrm = np.linalg.norm(w)
+    return w / nrm, reg.estimator_.intercept_ / nrm
+
+
+def road_plane_text(w, h):
+    """data_preprocessing/RANSAC.py:60-67."""
+    return "\n".join(["# Plane", "Width 4", "Height 1", "{:e} {:e} {:e} {:e}".format(w[0], w[1], w[2], h)])
+
+
+# ------------------------------------------------------------------------------------------
 # f-1  self-training merge (combine_labels.py)
 # ------------------------------------------------------------------------------------------
 def detections_to_boxes(preds):

@@ -473,3 +473,31 @@ def test_full_size_properties_lyft_shape():
     kept[0, :keep.sum()] = r.boxes[0, :nb][torch.from_numpy(keep).cuda()]
     keep2, _ = p.seed_nms(kept, torch.tensor([int(keep.sum())], dtype=torch.int32, device="cuda"))
     assert keep2.cpu().numpy()[0, :keep.sum()].all()
+
+
+@pytest.mark.parametrize("name", ["small", "nusc_small", "lyft60k_t2"])
+def test_road_plane_files(golden_case, name, tmp_path):
+    """the drop-in data_preprocessing/RANSAC.py against the file the reference's own
+    script wrote for the same scan and numpy stream."""
+    import os
+    from modest_b200 import synth
+    from modest_b200.data_preprocessing import RANSAC as road
+    case, shape, g = golden_case(name)
+    os.makedirs(tmp_path / "calib"); os.makedirs(tmp_path / "velodyne")
+    synth.write_calib(str(tmp_path / "calib" / "000000.txt"), case.calib)
+    case.query.tofile(tmp_path / "velodyne" / "000000.bin")
+    np.random.seed(77 + case.scan_id)
+    road.extract_ransac(str(tmp_path / "calib"), str(tmp_path / "velodyne"), str(tmp_path / "planes"),
+                        min_h=shape.sensor_height - 0.3, max_h=shape.sensor_height + 0.3)
+    text = (tmp_path / "planes" / "000000.txt").read_text()
+    got = np.array([float(v) for v in text.split("\n")[3].split()])
+    assert np.abs(got - g["road_plane"]).max() <= 1e-6          # '{:e}' keeps 7 significant digits
+    assert text == str(g["road_text"])
+    # too few candidates -> the script's default plane
+    w, h = road.road_plane(case.query[:3], ku_calib(g), 1.5, 2.0)
+    assert list(w) == [0.0, -1.0, 0.0] and h == 1.65
+
+
+def ku_calib(g):
+    from modest_b200.generate_cluster_mask.utils import kitti_util as ku
+    return ku.Calibration(dict(P2=g["calib_P2"], Tr_velo_to_cam=g["calib_V2C"], R0_rect=g["calib_R0"]))
