@@ -320,6 +320,14 @@ int modest_kitti_labels_host(const double* h_boxes, int n, const uint8_t* h_keep
                              const char* obj_type, const double* h_scores, char* h_text,
                              size_t text_cap, size_t* h_len, int* h_n_out,
                              uint8_t* h_kept_out);
+/* Batched form for the streaming engine: scan s owns h_n_boxes[s] rows at
+ * h_boxes + s*max_boxes*8, keep flags at h_keep + s*max_boxes (optional), P2 at h_P + s*12.
+ * The texts are written back to back into h_text; h_text_off (n_scans+1, i64) gets their offsets. */
+int modest_kitti_labels_batch_host(const double* h_boxes, const int32_t* h_n_boxes,
+                                   const uint8_t* h_keep, int n_scans, int max_boxes,
+                                   const double* h_P, int fov_only, int image_h, int image_w,
+                                   const char* obj_type, char* h_text, size_t text_cap,
+                                   int64_t* h_text_off);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,8 @@ SIGNATURES = {
     "modest_nms_bev": (C.c_int, [_vp, C.c_int, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "modest_nms_normal": (C.c_int, [_vp, C.c_int, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "modest_seed_nms_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _f32, _vp, _vp, _vp, _vp]),
+    "modest_kitti_labels_batch_host": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int,
+                                                 C.c_char_p, _vp, _sz, _vp]),
     "modest_kitti_labels_host": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_char_p,
                                            _vp, _vp, _sz, _vp, _vp, _vp]),
 }

@@ -91,3 +91,28 @@ extern "C" int modest_kitti_labels_host(const double* h_boxes, int n, const uint
   *h_n_out = lines;
   return MODEST_OK;
 }
+
+// Batched form: scan s has h_n_boxes[s] rows at h_boxes + s*max_boxes*8, keep flags at
+// h_keep + s*max_boxes (optional) and P2 at h_P + s*12.  Texts are written back to back into
+// h_text (no separators); h_text_off (n_scans+1) receives their byte offsets.
+extern "C" int modest_kitti_labels_batch_host(const double* h_boxes, const int32_t* h_n_boxes, const uint8_t* h_keep,
+                                              int n_scans, int max_boxes, const double* h_P, int fov_only, int image_h,
+                                              int image_w, const char* obj_type, char* h_text, size_t text_cap,
+                                              int64_t* h_text_off) {
+  MODEST_REQUIRE(h_n_boxes && h_P && h_text && h_text_off && (n_scans == 0 || h_boxes), "kitti_labels_batch: null pointer argument");
+  size_t pos = 0;
+  h_text_off[0] = 0;
+  for (int s = 0; s < n_scans; ++s) {
+    size_t len = 0;
+    int lines = 0;
+    MODEST_REQUIRE(pos < text_cap, "kitti_labels_batch: text buffer too small");
+    const int rc = modest_kitti_labels_host(h_boxes + (size_t)s * max_boxes * 8, h_n_boxes[s],
+                                            h_keep ? h_keep + (size_t)s * max_boxes : nullptr, h_P + (size_t)s * 12, fov_only,
+                                            image_h, image_w, obj_type, nullptr, h_text + pos, text_cap - pos, &len, &lines,
+                                            nullptr);
+    if (rc != MODEST_OK) return rc;
+    pos += len;
+    h_text_off[s + 1] = (int64_t)pos;
+  }
+  return MODEST_OK;
+}

@@ -33,6 +33,24 @@ class HostBatch:
     trav_sizes: list             # list (per scan) of lists (per traversal) of point counts
     calibs: list                 # per scan dict / Calibration
     scan_ids: list = field(default_factory=list)
+    _tables: dict = field(default_factory=dict, repr=False)
+
+    def tables(self):
+        """Offset tables and calibration rows, derived once per batch (host arrays)."""
+        if not self._tables:
+            q_sizes = self.q_sizes
+            trav_counts = [len(t) for t in self.trav_sizes]
+            h_sizes = [m for t in self.trav_sizes for m in t]
+            q_off = np.concatenate([[0], np.cumsum(q_sizes)]).astype(np.int64)
+            h_off = np.concatenate([[0], np.cumsum(h_sizes)]).astype(np.int64)
+            trav_off = np.concatenate([[0], np.cumsum(trav_counts)]).astype(np.int32)
+            count_off = np.concatenate([[0], np.cumsum(np.array(q_sizes, np.int64) * np.array(trav_counts, np.int64))]).astype(np.int64)
+            self._tables = dict(q_off=q_off, h_off=h_off, trav_off=trav_off, count_off=count_off,
+                                small=np.concatenate([q_off, h_off, count_off]).astype(np.int64),
+                                crow=np.stack([pl.calib_row(c) for c in self.calibs]),
+                                P2=np.stack([pl.calib_P2(c) for c in self.calibs]),
+                                max_q=max(q_sizes), max_h=max(h_sizes))
+        return self._tables
 
     @property
     def h2d_bytes(self):
@@ -105,15 +123,9 @@ class SeedLabelEngine:
     def _upload(self, slot: _Slot, hb: HostBatch):
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot.done)                # buffers free again?
-            q_sizes = hb.q_sizes
-            trav_counts = [len(t) for t in hb.trav_sizes]
-            h_sizes = [m for t in hb.trav_sizes for m in t]
-            q_off = np.concatenate([[0], np.cumsum(q_sizes)]).astype(np.int64)
-            h_off = np.concatenate([[0], np.cumsum(h_sizes)]).astype(np.int64)
-            trav_off = np.concatenate([[0], np.cumsum(trav_counts)]).astype(np.int32)
-            count_off = np.concatenate([[0], np.cumsum(np.array(q_sizes, np.int64) * np.array(trav_counts, np.int64))]).astype(np.int64)
-            small = np.concatenate([q_off, h_off, count_off]).astype(np.int64)
-            crow = np.stack([pl.calib_row(c) for c in hb.calibs])
+            tb = hb.tables()
+            q_off, h_off, trav_off, count_off, small, crow = (tb["q_off"], tb["h_off"], tb["trav_off"], tb["count_off"],
+                                                              tb["small"], tb["crow"])
             # the small tables go first and from pinned staging, so that enqueueing this upload
             # never blocks the host behind the bulk copies
             small_h = slot.pinned("off_h", small.shape, torch.int64)
@@ -136,12 +148,12 @@ class SeedLabelEngine:
             p.copy_(hb.ptc, non_blocking=True)
             a, b = len(q_off), len(q_off) + len(h_off)
             slot.pp_batch = pp_mod.PPBatch(
-                q, small_d[:a], h, small_d[a:b], trav_d, small_d[b:], n_scans=len(q_sizes), n_trav_total=int(trav_off[-1]),
-                n_query_total=int(q_off[-1]), n_count_total=int(count_off[-1]), max_query_points=max(q_sizes),
-                max_trav_points=max(h_sizes), h_q_off=q_off, h_trav_off=trav_off, h_count_off=count_off)
+                q, small_d[:a], h, small_d[a:b], trav_d, small_d[b:], n_scans=len(hb.q_sizes), n_trav_total=int(trav_off[-1]),
+                n_query_total=int(q_off[-1]), n_count_total=int(count_off[-1]), max_query_points=tb["max_q"],
+                max_trav_points=tb["max_h"], h_q_off=q_off, h_trav_off=trav_off, h_count_off=count_off)
             pp = slot.buf("pp", (int(q_off[-1]),), torch.float32)
             slot.scan_batch = pl.ScanBatch(ptc=p, off=small_d[:a], pp=pp, calib=calib_d,
-                                           P2=np.stack([pl.calib_P2(c) for c in hb.calibs]), h_off=q_off,
+                                           P2=tb["P2"], h_off=q_off,
                                            scan_ids=hb.scan_ids)
             slot.host = hb
             slot.ready.record(self.copy_stream)
@@ -168,7 +180,7 @@ class SeedLabelEngine:
         r, b = slot.result, slot.scan_batch
         hb_, hn, hk = r.h_boxes.numpy(), r.h_n.numpy(), r.h_keep.numpy()
         self.d2h_bytes_last = hb_.nbytes + hn.nbytes + hk.nbytes
-        return [self.pipe.format_labels(hb_[s, :hn[s]], hk[s, :hn[s]], b.P2[s])[0] for s in range(b.n_scans)]
+        return self.pipe.format_labels_batch(hb_, hn, hk, b.P2)
 
     def process(self, host_batches):
         """Generator: yields (scan_ids, [label text per scan]) for every batch, in order."""
@@ -181,15 +193,13 @@ class SeedLabelEngine:
         self._upload(self.slots[0], nxt)
         while nxt is not None:
             cur_slot = self.slots[step % 3]
-            cur = nxt
             nxt = next(it, None)
-            self._compute(cur_slot, step)
-            if nxt is not None:
+            if nxt is not None:          # start the next batch's DMA before spending host time on launches
                 self._upload(self.slots[(step + 1) % 3], nxt)
+            self._compute(cur_slot, step)
             if pending is not None:
                 yield pending.host.scan_ids, self._finish(pending)
             pending = cur_slot
             step += 1
-            del cur
         if pending is not None:
             yield pending.host.scan_ids, self._finish(pending)

@@ -374,7 +374,26 @@ class SeedLabelPipeline:
         h_boxes = boxes.cpu().numpy()
         h_n = n_boxes.cpu().numpy()
         h_keep = keep.cpu().numpy()
-        return [self.format_labels(h_boxes[s, :h_n[s]], h_keep[s, :h_n[s]], b.P2[s])[0] for s in range(b.n_scans)]
+        return self.format_labels_batch(h_boxes, h_n, h_keep, b.P2)
+
+    def format_labels_batch(self, h_boxes, h_n, h_keep, P2, obj_type="Dynamic"):
+        """All scans of a batch in one library call: h_boxes (S,max_boxes,8) f64, h_n (S) i32,
+        h_keep (S,max_boxes) u8, P2 (S,3,4) f64 -- host arrays -> list of S label texts."""
+        S, mb = int(h_boxes.shape[0]), int(h_boxes.shape[1])
+        h_boxes = np.ascontiguousarray(h_boxes, dtype=np.float64)
+        h_n = np.ascontiguousarray(h_n, dtype=np.int32)
+        h_keep = np.ascontiguousarray(h_keep, dtype=np.uint8)
+        P2 = np.ascontiguousarray(P2, dtype=np.float64)
+        cap = 256 * max(int(h_n.sum()), 1) + 16
+        buf = C.create_string_buffer(cap)
+        offs = np.zeros(S + 1, dtype=np.int64)
+        ish = self.cfg["image_shape"]
+        _lib.check(self.lib.modest_kitti_labels_batch_host(
+            h_boxes.ctypes.data_as(C.c_void_p), h_n.ctypes.data_as(C.c_void_p), h_keep.ctypes.data_as(C.c_void_p), S, mb,
+            P2.ctypes.data_as(C.c_void_p), 1 if self.cfg["fov_only"] else 0, int(ish[0]), int(ish[1]), obj_type.encode(),
+            buf, cap, offs.ctypes.data_as(C.c_void_p)), "modest_kitti_labels_batch_host")
+        raw = buf.raw
+        return [raw[offs[s]:offs[s + 1]].decode() for s in range(S)]
 
     def format_labels(self, boxes8, keep, P2, scores=None, obj_type="Dynamic"):
         n = int(boxes8.shape[0])
