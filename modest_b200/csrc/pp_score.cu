@@ -453,7 +453,9 @@ __global__ void __launch_bounds__(256) pp_entropy_kernel(
     for (int t = 0; t < T; ++t) tot += c[(size_t)t * n + k];
     const double denom = __dadd_rn((double)tot, 1e-8);
     const double acc = numpy_pairwise_sum(T, [&](int t) {
-      const double P = __ddiv_rn((double)c[(size_t)t * n + k], denom);
+      const int ct = c[(size_t)t * n + k];
+      if (ct == 0) return 0.0;                       // -0.0 * ln(1e-8) is exactly +0.0: skip the log
+      const double P = __ddiv_rn((double)ct, denom);
       return __dmul_rn(-P, log(__dadd_rn(P, 1e-8)));
     });
     pp[qbeg + orig] = (float)__ddiv_rn(acc, logT);

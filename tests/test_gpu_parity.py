@@ -352,6 +352,11 @@ def test_edge_cases_empty_ragged_and_degenerate():
         if len(q):
             want = orc.persistence_entropy(ref).astype(np.float32)
             assert np.allclose(pp[b.h_q_off[s]:b.h_q_off[s + 1]], want, atol=1e-6, equal_nan=True)
+    # --- removed (NaN-encoded) history rows, as the nuScenes centre removal produces, never count ---
+    hn = [np.concatenate([h0[0], np.full((7, 3), np.nan, np.float32)])[rng.permutation(157)], h0[2]]
+    _, c_nan = pp_score.count_neighbors_and_score(q0, hn, return_counts=True)
+    _, c_ref = pp_score.count_neighbors_and_score(q0, [h0[0], h0[2]], return_counts=True)
+    assert np.array_equal(c_nan, c_ref)
     # --- pipeline: a normal scan, a scan with no points, a scan that is ground only ---
     case = synth.make_scan_case(21, synth.LYFT, n_traversals=2, n_points=5000)
     g = rng.uniform(-30, 30, (3000, 2))
