@@ -248,7 +248,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     h2d_gbs = 4 * probe.numel() * 4 / (time.perf_counter() - tp) / 1e9
     del probe, probe_d
-    e2e_run(max(args.warmup, 4))          # every slot of the engine's 3-slot ring is touched before timing
+    e2e_run(max(args.warmup, 6))          # every slot of the engine's ring is touched before timing
     barrier()
     t0 = time.perf_counter()
     e2e_run(args.steps)

@@ -130,8 +130,15 @@ __device__ __forceinline__ void for_each_candidate(const float4* __restrict__ so
   const int lane = threadIdx.x & 31;
   const int xa = clampi(cx - L, 0, G - 1), xb = clampi(cx + L, 0, G - 1);
   const int ya = clampi(cy - L, 0, G - 1), yb = clampi(cy + L, 0, G - 1);
+  // lane r fetches the position range of window row r (windows are at most 32 rows tall), so
+  // the row loop below never waits on a dependent load of its own
+  int rkb = 0, rke = 0;
+  if (ya + lane <= yb) {
+    rkb = __ldg(cells + (ya + lane) * G + xa);
+    rke = __ldg(cells + (ya + lane) * G + xb + 1);
+  }
   for (int y = ya; y <= yb; ++y) {
-    const int kb = __ldg(cells + y * G + xa), ke = __ldg(cells + y * G + xb + 1);
+    const int kb = __shfl_sync(0xffffffffu, rkb, y - ya), ke = __shfl_sync(0xffffffffu, rke, y - ya);
     for (int k0 = kb; k0 < ke; k0 += 32) {
       const int k = k0 + lane;
       const bool live = k < ke && k != self_pos;
@@ -710,6 +717,7 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
   const double r2_max = radius * radius;
   int L_full = (int)ceil(radius / (double)kGraphCell - 1e-9);
   if (L_full < 1) L_full = 1;
+  MODEST_REQUIRE(L_full <= 15, "affinity_graph: radius %g spans more than 15 cells", radius);
   for (int L = 1; L < L_full && lv.n < 1; L *= 2) {        // one fine level measured best (profiles/README.md)
     lv.L[lv.n] = L;
     lv.r2[lv.n] = ((double)kGraphCell * L) * ((double)kGraphCell * L);

@@ -2,7 +2,7 @@
 
 `SeedLabelEngine.process(host_batches)` is the call a user of the fused path makes (the CLIs use
 the same stages one scan at a time for RNG parity).  It overlaps the three phases of consecutive
-batches on two CUDA streams:
+batches on separate CUDA streams:
 
     copy stream    : pinned host -> device copies of batch k+1
     compute streams: PP score + seed-label pipeline of batch k (two lanes, alternating batches)
@@ -110,11 +110,15 @@ class _Slot:
 
 
 class SeedLabelEngine:
-    def __init__(self, cfg=None, radius=0.3, grid_dim=512, max_clusters=2048, max_boxes=128, seed=0):
+    def __init__(self, cfg=None, radius=0.3, grid_dim=512, max_clusters=2048, max_boxes=128, seed=0, depth=2):
         self.copy_stream = torch.cuda.Stream()
-        # three slots: while batch k computes, batch k+1 uploads and batch k-1 is read back, and
-        # no slot is refilled before the host has finished with its previous contents
-        self.slots = [_Slot(cfg, radius, grid_dim, max_clusters, max_boxes) for _ in range(3)]
+        # `depth` batches may be computing while the host reads back an older one: the launches of
+        # batch k are enqueued before the host waits for batch k-depth, so two lanes of kernels
+        # are always queued and one batch's narrow kernels fill the other's gaps.  depth + 2 slots:
+        # one uploading, `depth` computing, one being read back -- no slot is refilled before the
+        # host has finished with its previous contents
+        self.depth = max(1, int(depth))
+        self.slots = [_Slot(cfg, radius, grid_dim, max_clusters, max_boxes) for _ in range(self.depth + 2)]
         self.pipe = self.slots[0].pipe
         self.seed = int(seed)
         self.d2h_bytes_last = 0
@@ -184,22 +188,24 @@ class SeedLabelEngine:
 
     def process(self, host_batches):
         """Generator: yields (scan_ids, [label text per scan]) for every batch, in order."""
-        pending = None
+        pending = []                     # slots whose kernels are enqueued, oldest first
         step = 0
+        n_slots = len(self.slots)
         it = iter(host_batches)
         nxt = next(it, None)
         if nxt is None:
             return
         self._upload(self.slots[0], nxt)
         while nxt is not None:
-            cur_slot = self.slots[step % 3]
+            cur_slot = self.slots[step % n_slots]
             nxt = next(it, None)
             if nxt is not None:          # start the next batch's DMA before spending host time on launches
-                self._upload(self.slots[(step + 1) % 3], nxt)
+                self._upload(self.slots[(step + 1) % n_slots], nxt)
             self._compute(cur_slot, step)
-            if pending is not None:
-                yield pending.host.scan_ids, self._finish(pending)
-            pending = cur_slot
+            pending.append(cur_slot)
+            if len(pending) > self.depth:
+                done = pending.pop(0)
+                yield done.host.scan_ids, self._finish(done)
             step += 1
-        if pending is not None:
-            yield pending.host.scan_ids, self._finish(pending)
+        for done in pending:
+            yield done.host.scan_ids, self._finish(done)
