@@ -233,7 +233,7 @@ __device__ __forceinline__ bool kth_by_histogram(Scan scan, int k_nn, T R2, int*
 
 constexpr int kKnnWarps = 4;
 constexpr int kMaxLevels = 4;
-struct KnnLevels { int n; int L[kMaxLevels]; double r2[kMaxLevels]; };   // windows of +-L cells, radius^2 they cover
+struct KnnLevels { int n; int min_pop; int L[kMaxLevels]; double r2[kMaxLevels]; };   // windows of +-L cells, radius^2 they cover
 constexpr int kListCap = 1024;      // (f32 d2, sorted position) pairs cached per warp between the passes
 
 // One warp per point.  Pass A sweeps the cell window once, evaluating d2 in float32 and caching
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
         int tot = 0;
         if (ya + lane <= yb) tot = __ldg(cells + (ya + lane) * G + xb + 1) - __ldg(cells + (ya + lane) * G + xa);
         tot = warp_sum(tot);                             // windows are at most 32 rows tall
-        if (tot <= k_nn) continue;
+        if (tot <= lv.min_pop) continue;
       }
       // f32 evaluation error of d2 (coordinates up to ~1e2 m, d2 <= R2): a few ulps of d2 plus
       // the rounding of the coordinate differences; eps is a safe absolute bound
@@ -536,9 +536,13 @@ __global__ void __launch_bounds__(256) dbscan_union_kernel(
     if (!core[base + i]) continue;                 // warp-uniform
     const int m = nbr_cnt[base + i];
     const size_t row = (size_t)(base + i) * k_nn;
+    // after the initial forest and the pointer-doubling sweeps most points hang directly under
+    // their root: two points with the same parent are already together (parents never leave
+    // their tree), which spares the two dependent find() walks for almost every edge
+    const int pi = parent[base + i];
     for (int c = lane; c < m; c += 32) {
       const int j = nbr[row + c];
-      if (j < i && core[base + j] && (double)nbr_w[row + c] <= eps) uf_union(parent + base, i, j);
+      if (j < i && (double)nbr_w[row + c] <= eps && core[base + j] && parent[base + j] != pi) uf_union(parent + base, i, j);
     }
   }
 }
@@ -718,7 +722,17 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
   int L_full = (int)ceil(radius / (double)kGraphCell - 1e-9);
   if (L_full < 1) L_full = 1;
   MODEST_REQUIRE(L_full <= 15, "affinity_graph: radius %g spans more than 15 cells", radius);
-  for (int L = 1; L < L_full && lv.n < 1; L *= 2) {        // one fine level measured best (profiles/README.md)
+  // fine levels (windows of +-L cells, tried in order before the full radius) and the window
+  // population, in multiples of k, below which a fine level is not even tried.  One level of
+  // +-2 cells tried from 2k points up measured best on the Lyft shape (4.14 -> 3.97 ms per
+  // 12-scan step against {+-1 cell, from k points}; more levels gain nothing).
+  static const int kFineLevels[] = {2};
+  const int fine_n = (int)(sizeof(kFineLevels) / sizeof(kFineLevels[0]));
+  const int* fine = kFineLevels;
+  const double try_factor = 2.0;
+  for (int i = 0; i < fine_n; ++i) {
+    const int L = fine[i];
+    if (L < 1 || L >= L_full) continue;
     lv.L[lv.n] = L;
     lv.r2[lv.n] = ((double)kGraphCell * L) * ((double)kGraphCell * L);
     ++lv.n;
@@ -726,6 +740,7 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
   lv.L[lv.n] = L_full;
   lv.r2[lv.n] = r2_max;
   ++lv.n;
+  lv.min_pop = (int)ceil(try_factor * n_neighbors);
   int wblocks = (int)((max_points + 3) / 4);
   if (wblocks < 1) wblocks = 1;
   if (wblocks > 148 * 16) wblocks = 148 * 16;
