@@ -185,6 +185,11 @@ int modest_ground_mask_batch(const float* d_ptc, int point_stride, const int64_t
  * row d_off[s]+i and holds d_nbr_cnt entries (unordered) of d_nbr (neighbour index within the
  * kept list) and d_nbr_w.  *d_flags (one i32) gets bit0/bit1 set if distance ties made a
  * k-th neighbour ambiguous / overflowed a row (never on duplicate-free data).
+ *   partition_eps / d_nbr_eps_cnt  optional (pass a negative value / NULL to switch off): the
+ *                 caller announces the DBSCAN radius it will use; every row then lists the edges
+ *                 with (double)w <= partition_eps first and d_nbr_eps_cnt (NP) i32 receives their
+ *                 number (-1 for rows left unpartitioned).  The order of the entries of a row
+ *                 carries no other meaning (the reference's CSR is rebuilt sorted by column).
  * ------------------------------------------------------------------------------------------ */
 size_t modest_graph_workspace_bytes(int n_scans, int64_t n_points_total, int n_neighbors,
                                     int grid_dim);
@@ -192,7 +197,8 @@ int modest_affinity_graph_batch(const float* d_kept, const int64_t* d_off,
                                 const int32_t* d_n_kept, int n_scans, int64_t n_points_total,
                                 int64_t max_points, int n_neighbors, double radius,
                                 int grid_dim, int32_t* d_nbr, float* d_nbr_w,
-                                int32_t* d_nbr_cnt, int32_t* d_flags, void* d_ws,
+                                int32_t* d_nbr_cnt, double partition_eps,
+                                int32_t* d_nbr_eps_cnt, int32_t* d_flags, void* d_ws,
                                 size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -202,6 +208,8 @@ int modest_affinity_graph_batch(const float* d_kept, const int64_t* d_off,
  * its size >= min_samples; clusters = connected components of core-core edges, numbered by
  * their smallest member index; a border point takes the smallest cluster id among its core
  * neighbours; everything else -1.
+ *   d_nbr_eps_cnt optional (NULL = scan the weights): the prefix counts written by
+ *                 modest_affinity_graph_batch called with partition_eps == eps
  *   d_labels_kept (NP) i32 out: label per kept point;  d_labels_full (NP) i32 out: label per
  *   original point (-1 for removed points), i.e. the `labels` array of generate_mask.py:76-81
  *   d_n_clusters  (n_scans) i32 out
@@ -210,7 +218,8 @@ size_t modest_dbscan_workspace_bytes(int64_t n_points_total);
 int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept,
                         const int32_t* d_kept_idx, int n_scans, int64_t n_points_total,
                         int64_t max_points, int n_neighbors, const int32_t* d_nbr,
-                        const float* d_nbr_w, const int32_t* d_nbr_cnt, double eps,
+                        const float* d_nbr_w, const int32_t* d_nbr_cnt,
+                        const int32_t* d_nbr_eps_cnt, double eps,
                         int min_samples, int32_t* d_labels_kept, int32_t* d_labels_full,
                         int32_t* d_n_clusters, void* d_ws, size_t ws_bytes, void* stream);
 

@@ -45,9 +45,9 @@ SIGNATURES = {
                                            _vp, _vp, _vp]),
     "modest_graph_workspace_bytes": (_sz, [C.c_int, _i64, C.c_int, C.c_int]),
     "modest_affinity_graph_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, C.c_int, _f64, C.c_int,
-                                              _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                              _vp, _vp, _vp, _f64, _vp, _vp, _vp, _sz, _vp]),
     "modest_dbscan_workspace_bytes": (_sz, [_i64]),
-    "modest_dbscan_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, C.c_int, _vp, _vp, _vp, _f64,
+    "modest_dbscan_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, _f64,
                                       C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "modest_filter_workspace_bytes": (_sz, [C.c_int, _i64, C.c_int]),
     "modest_filter_and_fit_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _i64, _i64,

@@ -404,57 +404,105 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
 }
 
 // ---- H.2: mutual test + L1 pp weights -------------------------------------------------------------
+// Row i keeps j iff i is also within j's k-th neighbour distance.  When the caller announces the
+// DBSCAN radius (eps_first >= 0), the edges with (double)w <= eps_first are written first and
+// their number goes to nbr_eps_cnt: the DBSCAN kernels then touch only that prefix of every row
+// and never read the weights (order within a row carries no meaning; rows of more than 96 slots
+// are left unpartitioned and get nbr_eps_cnt = -1).
+constexpr int kMutualChunks = 3;        // 32-lane chunks held in registers for the partition
+
 __global__ void __launch_bounds__(256) mutual_edges_kernel(
     const float4* __restrict__ kept, const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept,
     int k_nn, const double* __restrict__ rk2, const int32_t* __restrict__ knn, const int32_t* __restrict__ knn_cnt,
-    int32_t* __restrict__ nbr, float* __restrict__ nbr_w, int32_t* __restrict__ nbr_cnt) {
+    int32_t* __restrict__ nbr, float* __restrict__ nbr_w, int32_t* __restrict__ nbr_cnt, double eps_first,
+    int32_t* __restrict__ nbr_eps_cnt) {
   const int s = blockIdx.y;
   const int n = n_kept[s];
   const int64_t base = off[s];
   const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const bool partition = nbr_eps_cnt != nullptr && eps_first >= 0.0 && k_nn <= 32 * kMutualChunks;
   for (int i = warp; i < n; i += nwarps) {
     const float4 p = kept[base + i];
     const int m = knn_cnt[base + i];
     const int32_t* row = knn + (size_t)(base + i) * k_nn;
+    int32_t* orow = nbr + (size_t)(base + i) * k_nn;
+    float* wrow = nbr_w + (size_t)(base + i) * k_nn;
+    auto candidate = [&](int c, int& j, float& w) {
+      j = 0; w = 0.f;
+      if (c >= m) return false;
+      j = row[c];
+      const float4 q = kept[base + j];
+      const double d2 = sqdist_f64_seq(q.x, q.y, q.z, p.x, p.y, p.z);   // same expression as row j used
+      w = fabsf(__fsub_rn(p.w, q.w));
+      return d2 <= rk2[base + j];
+    };
+    if (partition) {
+      int jj[kMutualChunks];
+      float ww[kMutualChunks];
+      unsigned bal_e[kMutualChunks], bal_o[kMutualChunks];
+      int n_e = 0, n_o = 0;
+#pragma unroll
+      for (int t = 0; t < kMutualChunks; ++t) {
+        const bool in = candidate(32 * t + lane, jj[t], ww[t]);
+        const bool e = in && (double)ww[t] <= eps_first;
+        bal_e[t] = __ballot_sync(0xffffffffu, e);
+        bal_o[t] = __ballot_sync(0xffffffffu, in && !e);
+        n_e += __popc(bal_e[t]);
+        n_o += __popc(bal_o[t]);
+      }
+      int have_e = 0, have_o = n_e;
+#pragma unroll
+      for (int t = 0; t < kMutualChunks; ++t) {
+        const unsigned me = 1u << lane;
+        int slot = -1;
+        if (bal_e[t] & me) slot = have_e + __popc(bal_e[t] & lt);
+        else if (bal_o[t] & me) slot = have_o + __popc(bal_o[t] & lt);
+        if (slot >= 0) { orow[slot] = jj[t]; wrow[slot] = ww[t]; }
+        have_e += __popc(bal_e[t]);
+        have_o += __popc(bal_o[t]);
+      }
+      if (lane == 0) { nbr_cnt[base + i] = n_e + n_o; nbr_eps_cnt[base + i] = n_e; }
+      continue;
+    }
     int have = 0;
     for (int c0 = 0; c0 < m; c0 += 32) {
-      const int c = c0 + lane;
-      bool in = false;
-      int j = 0;
-      float w = 0.f;
-      if (c < m) {
-        j = row[c];
-        const float4 q = kept[base + j];
-        const double d2 = sqdist_f64_seq(q.x, q.y, q.z, p.x, p.y, p.z);   // same expression as row j used
-        in = d2 <= rk2[base + j];
-        w = fabsf(__fsub_rn(p.w, q.w));
-      }
+      int j;
+      float w;
+      const bool in = candidate(c0 + lane, j, w);
       const unsigned bal = __ballot_sync(0xffffffffu, in);
       if (in) {
-        const int slot = have + __popc(bal & ((1u << lane) - 1u));
-        nbr[(size_t)(base + i) * k_nn + slot] = j;
-        nbr_w[(size_t)(base + i) * k_nn + slot] = w;
+        const int slot = have + __popc(bal & lt);
+        orow[slot] = j;
+        wrow[slot] = w;
       }
       have += __popc(bal);
     }
-    if (lane == 0) nbr_cnt[base + i] = have;
+    if (lane == 0) {
+      nbr_cnt[base + i] = have;
+      if (nbr_eps_cnt) nbr_eps_cnt[base + i] = -1;
+    }
   }
 }
 
 // ---- I: DBSCAN ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dbscan_core_kernel(
     const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, int k_nn, const float* __restrict__ nbr_w,
-    const int32_t* __restrict__ nbr_cnt, double eps, int min_samples, uint8_t* __restrict__ core,
-    int32_t* __restrict__ parent) {
+    const int32_t* __restrict__ nbr_cnt, const int32_t* __restrict__ eps_cnt, double eps, int min_samples,
+    uint8_t* __restrict__ core, int32_t* __restrict__ parent) {
   const int s = blockIdx.y;
   const int n = n_kept[s];
   const int64_t base = off[s];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int m = nbr_cnt[base + i];
-    const float* w = nbr_w + (size_t)(base + i) * k_nn;
     int deg = 1;                                   // the point itself (sklearn adds the diagonal)
-    for (int c = 0; c < m; ++c) deg += ((double)w[c] <= eps);
+    const int pre = eps_cnt ? eps_cnt[base + i] : -1;
+    if (pre >= 0) deg += pre;                      // rows partitioned by mutual_edges_kernel
+    else {
+      const int m = nbr_cnt[base + i];
+      const float* w = nbr_w + (size_t)(base + i) * k_nn;
+      for (int c = 0; c < m; ++c) deg += ((double)w[c] <= eps);
+    }
     core[base + i] = deg >= min_samples;
     parent[base + i] = i;
   }
@@ -486,8 +534,8 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
 // union sweep below mostly finds "already together".
 __global__ void __launch_bounds__(256) dbscan_init_kernel(
     const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, int k_nn, const int32_t* __restrict__ nbr,
-    const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt, double eps, const uint8_t* __restrict__ core,
-    int32_t* __restrict__ parent) {
+    const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt, const int32_t* __restrict__ eps_cnt, double eps,
+    const uint8_t* __restrict__ core, int32_t* __restrict__ parent) {
   const int s = blockIdx.y;
   const int n = n_kept[s];
   const int64_t base = off[s];
@@ -495,12 +543,13 @@ __global__ void __launch_bounds__(256) dbscan_init_kernel(
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int i = warp; i < n; i += nwarps) {
     if (!core[base + i]) continue;
-    const int m = nbr_cnt[base + i];
+    const int pre = eps_cnt ? eps_cnt[base + i] : -1;      // >= 0: only this prefix holds eps-edges
+    const int m = pre >= 0 ? pre : nbr_cnt[base + i];
     const size_t row = (size_t)(base + i) * k_nn;
     int best = i;
     for (int c = lane; c < m; c += 32) {
       const int j = nbr[row + c];
-      if (j < best && core[base + j] && (double)nbr_w[row + c] <= eps) best = j;
+      if (j < best && (pre >= 0 || (double)nbr_w[row + c] <= eps) && core[base + j]) best = j;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -525,8 +574,8 @@ __global__ void __launch_bounds__(256) dbscan_jump_kernel(const int64_t* __restr
 // united once (from its larger endpoint)
 __global__ void __launch_bounds__(256) dbscan_union_kernel(
     const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, int k_nn, const int32_t* __restrict__ nbr,
-    const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt, double eps, const uint8_t* __restrict__ core,
-    int32_t* __restrict__ parent) {
+    const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt, const int32_t* __restrict__ eps_cnt, double eps,
+    const uint8_t* __restrict__ core, int32_t* __restrict__ parent) {
   const int s = blockIdx.y;
   const int n = n_kept[s];
   const int64_t base = off[s];
@@ -534,7 +583,8 @@ __global__ void __launch_bounds__(256) dbscan_union_kernel(
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int i = warp; i < n; i += nwarps) {
     if (!core[base + i]) continue;                 // warp-uniform
-    const int m = nbr_cnt[base + i];
+    const int pre = eps_cnt ? eps_cnt[base + i] : -1;
+    const int m = pre >= 0 ? pre : nbr_cnt[base + i];
     const size_t row = (size_t)(base + i) * k_nn;
     // after the initial forest and the pointer-doubling sweeps most points hang directly under
     // their root: two points with the same parent are already together (parents never leave
@@ -542,7 +592,8 @@ __global__ void __launch_bounds__(256) dbscan_union_kernel(
     const int pi = parent[base + i];
     for (int c = lane; c < m; c += 32) {
       const int j = nbr[row + c];
-      if (j < i && (double)nbr_w[row + c] <= eps && core[base + j] && parent[base + j] != pi) uf_union(parent + base, i, j);
+      if (j < i && (pre >= 0 || (double)nbr_w[row + c] <= eps) && core[base + j] && parent[base + j] != pi)
+        uf_union(parent + base, i, j);
     }
   }
 }
@@ -608,9 +659,9 @@ __global__ void __launch_bounds__(256) dbscan_label_cores_kernel(
 
 __global__ void __launch_bounds__(256) dbscan_label_borders_kernel(
     const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept, const int32_t* __restrict__ kept_idx, int k_nn,
-    const int32_t* __restrict__ nbr, const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt, double eps,
-    const uint8_t* __restrict__ core, const int32_t* __restrict__ labels_kept, int32_t* __restrict__ border_lab,
-    int32_t* __restrict__ labels_full) {
+    const int32_t* __restrict__ nbr, const float* __restrict__ nbr_w, const int32_t* __restrict__ nbr_cnt,
+    const int32_t* __restrict__ eps_cnt, double eps, const uint8_t* __restrict__ core, const int32_t* __restrict__ labels_kept,
+    int32_t* __restrict__ border_lab, int32_t* __restrict__ labels_full) {
   const int s = blockIdx.y;
   const int n = n_kept[s];
   const int64_t base = off[s];
@@ -620,11 +671,12 @@ __global__ void __launch_bounds__(256) dbscan_label_borders_kernel(
       lab = labels_kept[base + i];
     } else {
       lab = 0x7fffffff;
-      const int m = nbr_cnt[base + i];
+      const int pre = eps_cnt ? eps_cnt[base + i] : -1;
+      const int m = pre >= 0 ? pre : nbr_cnt[base + i];
       const size_t row = (size_t)(base + i) * k_nn;
       for (int c = 0; c < m; ++c) {
         const int j = nbr[row + c];
-        if (core[base + j] && (double)nbr_w[row + c] <= eps) lab = min(lab, labels_kept[base + j]);
+        if ((pre >= 0 || (double)nbr_w[row + c] <= eps) && core[base + j]) lab = min(lab, labels_kept[base + j]);
       }
       if (lab == 0x7fffffff) lab = -1;
       border_lab[base + i] = lab;       // labels_kept of cores is still being read by other threads
@@ -689,7 +741,7 @@ extern "C" size_t modest_graph_workspace_bytes(int n_scans, int64_t n_points_tot
 extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d_off, const int32_t* d_n_kept,
                                            int n_scans, int64_t n_points_total, int64_t max_points,
                                            int n_neighbors, double radius, int grid_dim, int32_t* d_nbr,
-                                           float* d_nbr_w, int32_t* d_nbr_cnt, int32_t* d_flags, void* d_ws,
+                                           float* d_nbr_w, int32_t* d_nbr_cnt, double partition_eps, int32_t* d_nbr_eps_cnt, int32_t* d_flags, void* d_ws,
                                            size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scans <= 0 || n_points_total <= 0) return MODEST_OK;
@@ -753,7 +805,7 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
   if (mblocks > 148 * 8) mblocks = 148 * 8;
   mutual_edges_kernel<<<dim3(mblocks, n_scans), 256, 0, stream>>>(reinterpret_cast<const float4*>(d_kept), d_off,
                                                                  d_n_kept, n_neighbors, rk2, knn, knn_cnt, d_nbr,
-                                                                 d_nbr_w, d_nbr_cnt);
+                                                                 d_nbr_w, d_nbr_cnt, partition_eps, d_nbr_eps_cnt);
   MODEST_LAUNCH_CHECK("mutual_edges_kernel");
   note_launch(2);
   return MODEST_OK;
@@ -765,7 +817,7 @@ extern "C" size_t modest_dbscan_workspace_bytes(int64_t n_points_total) {
 
 extern "C" int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept, const int32_t* d_kept_idx,
                                    int n_scans, int64_t n_points_total, int64_t max_points, int n_neighbors,
-                                   const int32_t* d_nbr, const float* d_nbr_w, const int32_t* d_nbr_cnt, double eps,
+                                   const int32_t* d_nbr, const float* d_nbr_w, const int32_t* d_nbr_cnt, const int32_t* d_nbr_eps_cnt, double eps,
                                    int min_samples, int32_t* d_labels_kept, int32_t* d_labels_full,
                                    int32_t* d_n_clusters, void* d_ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -783,20 +835,20 @@ extern "C" int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept
   int pblocks = (int)((max_points + 255) / 256);
   if (pblocks < 1) pblocks = 1;
   dbscan_core_kernel<<<dim3(pblocks, n_scans), 256, 0, stream>>>(d_off, d_n_kept, n_neighbors, d_nbr_w, d_nbr_cnt,
-                                                                eps, min_samples, core, parent);
+                                                                d_nbr_eps_cnt, eps, min_samples, core, parent);
   MODEST_LAUNCH_CHECK("dbscan_core_kernel");
   int64_t eb = (max_points * 32 + 255) / 256;          // one warp per row
   if (eb < 1) eb = 1;
   if (eb > 148 * 16) eb = 148 * 16;
   dbscan_init_kernel<<<dim3((unsigned)eb, n_scans), 256, 0, stream>>>(d_off, d_n_kept, n_neighbors, d_nbr, d_nbr_w,
-                                                                     d_nbr_cnt, eps, core, parent);
+                                                                     d_nbr_cnt, d_nbr_eps_cnt, eps, core, parent);
   MODEST_LAUNCH_CHECK("dbscan_init_kernel");
   for (int r = 0; r < 4; ++r) {
     dbscan_jump_kernel<<<dim3(pblocks, n_scans), 256, 0, stream>>>(d_off, d_n_kept, parent);
     MODEST_LAUNCH_CHECK("dbscan_jump_kernel");
   }
   dbscan_union_kernel<<<dim3((unsigned)eb, n_scans), 256, 0, stream>>>(d_off, d_n_kept, n_neighbors, d_nbr, d_nbr_w,
-                                                                      d_nbr_cnt, eps, core, parent);
+                                                                      d_nbr_cnt, d_nbr_eps_cnt, eps, core, parent);
   MODEST_LAUNCH_CHECK("dbscan_union_kernel");
   dbscan_rank_roots_kernel<<<n_scans, 1024, 0, stream>>>(d_off, d_n_kept, core, parent, root_rank, d_n_clusters);
   MODEST_LAUNCH_CHECK("dbscan_rank_roots_kernel");
@@ -804,8 +856,8 @@ extern "C" int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept
   dbscan_label_cores_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_n_kept, core, parent, root_rank, d_labels_kept, d_labels_full);
   MODEST_LAUNCH_CHECK("dbscan_label_cores_kernel");
   // root_rank entries of non-root points are free: reuse the array for the border labels
-  dbscan_label_borders_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_n_kept, d_kept_idx, n_neighbors, d_nbr, d_nbr_w, d_nbr_cnt, eps,
-                                                        core, d_labels_kept, border_lab, d_labels_full);
+  dbscan_label_borders_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_n_kept, d_kept_idx, n_neighbors, d_nbr, d_nbr_w, d_nbr_cnt,
+                                                        d_nbr_eps_cnt, eps, core, d_labels_kept, border_lab, d_labels_full);
   MODEST_LAUNCH_CHECK("dbscan_label_borders_kernel");
   dbscan_merge_borders_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_n_kept, core, border_lab, d_labels_kept);
   MODEST_LAUNCH_CHECK("dbscan_merge_borders_kernel");

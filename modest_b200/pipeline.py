@@ -247,7 +247,9 @@ class SeedLabelPipeline:
         return kept, kept_idx, n_kept, mask
 
     # ------------------------------------------------------------------ stage H
-    def affinity_graph(self, kept, off, n_kept, n_scans, n_points, max_points, stream=None):
+    def affinity_graph(self, kept, off, n_kept, n_scans, n_points, max_points, stream=None, partition_eps=None):
+        """Returns nbr, nbr_w, nbr_cnt, flags.  With `partition_eps` (the DBSCAN radius the caller
+        will use) every row lists its eps-edges first and `self.nbr_eps_cnt` holds their number."""
         dev = kept.device
         g = self.cfg["graph"]
         k = int(g["n_neighbors"])
@@ -255,16 +257,19 @@ class SeedLabelPipeline:
         nbr_w = self._scr.get("nbr_w", n_points * k, torch.float32, dev)
         nbr_cnt = self._scr.get("nbr_cnt", n_points, torch.int32, dev)
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.nbr_eps_cnt = self._scr.get("nbr_eps_cnt", n_points, torch.int32, dev) if partition_eps is not None else None
         need = self.lib.modest_graph_workspace_bytes(n_scans, n_points, k, self.graph_grid)
         ws = self._scr.get("graph_ws", need, torch.uint8, dev)
         _lib.check(self.lib.modest_affinity_graph_batch(
             _lib.ptr(kept), _lib.ptr(off), _lib.ptr(n_kept), n_scans, n_points, max_points, k, float(g["radius"]),
-            self.graph_grid, _lib.ptr(nbr), _lib.ptr(nbr_w), _lib.ptr(nbr_cnt), _lib.ptr(flags), _lib.ptr(ws),
+            self.graph_grid, _lib.ptr(nbr), _lib.ptr(nbr_w), _lib.ptr(nbr_cnt),
+            -1.0 if partition_eps is None else float(partition_eps), _lib.ptr(self.nbr_eps_cnt), _lib.ptr(flags), _lib.ptr(ws),
             ws.numel(), _lib.stream_ptr(stream)), "modest_affinity_graph_batch")
         return nbr, nbr_w, nbr_cnt, flags
 
     # ------------------------------------------------------------------ stage I
-    def dbscan(self, off, n_kept, kept_idx, n_scans, n_points, max_points, nbr, nbr_w, nbr_cnt, stream=None):
+    def dbscan(self, off, n_kept, kept_idx, n_scans, n_points, max_points, nbr, nbr_w, nbr_cnt, stream=None,
+               nbr_eps_cnt=None):
         dev = off.device
         d = self.cfg["clustering"]["DBSCAN"]
         k = int(self.cfg["graph"]["n_neighbors"])
@@ -275,7 +280,7 @@ class SeedLabelPipeline:
         ws = self._scr.get("dbscan_ws", need, torch.uint8, dev)
         _lib.check(self.lib.modest_dbscan_batch(
             _lib.ptr(off), _lib.ptr(n_kept), _lib.ptr(kept_idx), n_scans, n_points, max_points, k, _lib.ptr(nbr),
-            _lib.ptr(nbr_w), _lib.ptr(nbr_cnt), float(d["eps"]), int(d["min_samples"]), _lib.ptr(labels_kept),
+            _lib.ptr(nbr_w), _lib.ptr(nbr_cnt), _lib.ptr(nbr_eps_cnt), float(d["eps"]), int(d["min_samples"]), _lib.ptr(labels_kept),
             _lib.ptr(labels_full), _lib.ptr(n_clusters), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(stream)),
             "modest_dbscan_batch")
         return labels_kept, labels_full, n_clusters
@@ -334,10 +339,12 @@ class SeedLabelPipeline:
         r.plane, r.ransac_info = self.fit_planes(b, pe["max_hs"], pe["range"], rng=rng, seed=seed, stream=stream)
         kept, r.kept_idx, r.n_kept, r.mask = self.ground_masks(
             b, r.plane, pe["offset"], pe["range"], cfg["limit_range"], want_mask=want_debug, stream=stream)
+        eps = float(cfg["clustering"]["DBSCAN"]["eps"])
         nbr, nbr_w, nbr_cnt, gflags = self.affinity_graph(kept, b.off, r.n_kept, b.n_scans, b.n_points,
-                                                          b.max_points, stream=stream)
+                                                          b.max_points, stream=stream, partition_eps=eps)
         _, r.labels_raw, r.n_clusters = self.dbscan(b.off, r.n_kept, r.kept_idx, b.n_scans, b.n_points,
-                                                    b.max_points, nbr, nbr_w, nbr_cnt, stream=stream)
+                                                    b.max_points, nbr, nbr_w, nbr_cnt, stream=stream,
+                                                    nbr_eps_cnt=self.nbr_eps_cnt)
         r.plane2, r.ransac_info2 = self.fit_planes(b, FILTER_PLANE["max_hs"], FILTER_PLANE["range"], rng=rng,
                                                    seed=seed + 0x9E3779B9, stream=stream)
         r.labels_filtered, r.labels, r.boxes, r.n_boxes, _, fflags = self.filter_and_fit(

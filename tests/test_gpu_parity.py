@@ -72,6 +72,44 @@ def test_masks_graph_dbscan_given_reference_plane(golden_case, name):
 
 
 @pytest.mark.parametrize("name", CASES)
+def test_eps_partitioned_rows_give_the_same_graph_and_labels(golden_case, name):
+    """The fused path asks the graph stage to list every row's eps-edges first
+    (modest_affinity_graph_batch partition_eps): same edge set, prefix = exactly the edges with
+    (double)w <= eps, and DBSCAN on the prefixes equals DBSCAN on the weights."""
+    case, shape, g = golden_case(name)
+    p = pl.SeedLabelPipeline(_cfg(shape))
+    b = _batch(case, g["pp"])
+    plane = torch.from_numpy(g["plane"][None].copy()).cuda()
+    kept, kept_idx, n_kept, _ = p.ground_masks(b, plane, 0.05, [[-70, 70], [-20, 20]], [[-70, 70], [-40, 40]])
+    nk = int(n_kept.cpu()[0])
+    k, eps = 70, 0.1
+    nbr, nbr_w, nbr_cnt, _ = p.affinity_graph(kept, b.off, n_kept, 1, b.n_points, b.max_points)
+    a_idx = nbr.cpu().numpy()[:nk * k].reshape(nk, k).copy()
+    a_w = nbr_w.cpu().numpy()[:nk * k].reshape(nk, k).copy()
+    a_cnt = nbr_cnt.cpu().numpy()[:nk].copy()
+    nbr, nbr_w, nbr_cnt, _ = p.affinity_graph(kept, b.off, n_kept, 1, b.n_points, b.max_points, partition_eps=eps)
+    b_idx = nbr.cpu().numpy()[:nk * k].reshape(nk, k)
+    b_w = nbr_w.cpu().numpy()[:nk * k].reshape(nk, k)
+    b_cnt = nbr_cnt.cpu().numpy()[:nk]
+    pre = p.nbr_eps_cnt.cpu().numpy()[:nk]
+    assert np.array_equal(a_cnt, b_cnt)
+    slot = np.arange(k)[None, :]
+    live = slot < b_cnt[:, None]
+    is_eps = b_w.astype(np.float64) <= eps
+    assert np.array_equal(pre, (is_eps & live).sum(1))
+    assert np.all(is_eps[live & (slot < pre[:, None])]) and not np.any(is_eps[live & (slot >= pre[:, None])])
+    big = np.iinfo(np.int32).max
+    oa = np.argsort(np.where(slot < a_cnt[:, None], a_idx, big), axis=1, kind="stable")
+    ob = np.argsort(np.where(live, b_idx, big), axis=1, kind="stable")
+    assert np.array_equal(np.take_along_axis(a_idx, oa, 1)[live], np.take_along_axis(b_idx, ob, 1)[live])
+    assert np.array_equal(np.take_along_axis(a_w, oa, 1)[live], np.take_along_axis(b_w, ob, 1)[live])
+    _, labels_full, n_clusters = p.dbscan(b.off, n_kept, kept_idx, 1, b.n_points, b.max_points, nbr, nbr_w, nbr_cnt,
+                                          nbr_eps_cnt=p.nbr_eps_cnt)
+    assert np.array_equal(labels_full.cpu().numpy(), g["labels_raw"])
+    assert int(n_clusters.cpu()[0]) == g["labels_raw"].max() + 1
+
+
+@pytest.mark.parametrize("name", CASES)
 def test_graph_edges_vs_oracle(golden_case, name):
     if name == "lyft60k_t2":
         pytest.skip("edge-by-edge compare runs on the small cases; the 60k case checks degrees + DBSCAN labels")
