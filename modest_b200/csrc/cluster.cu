@@ -445,12 +445,15 @@ __global__ void __launch_bounds__(256) mutual_edges_kernel(
       int n_e = 0, n_o = 0;
 #pragma unroll
       for (int t = 0; t < kMutualChunks; ++t) {
-        const bool in = candidate(32 * t + lane, jj[t], ww[t]);
-        const bool e = in && (double)ww[t] <= eps_first;
-        bal_e[t] = __ballot_sync(0xffffffffu, e);
-        bal_o[t] = __ballot_sync(0xffffffffu, in && !e);
-        n_e += __popc(bal_e[t]);
-        n_o += __popc(bal_o[t]);
+        bal_e[t] = bal_o[t] = 0u;
+        if (32 * t < m) {                                   // warp-uniform
+          const bool in = candidate(32 * t + lane, jj[t], ww[t]);
+          const bool e = in && (double)ww[t] <= eps_first;
+          bal_e[t] = __ballot_sync(0xffffffffu, e);
+          bal_o[t] = __ballot_sync(0xffffffffu, in && !e);
+          n_e += __popc(bal_e[t]);
+          n_o += __popc(bal_o[t]);
+        }
       }
       int have_e = 0, have_o = n_e;
 #pragma unroll
