@@ -243,14 +243,18 @@ constexpr int kListCap = 1024;      // (f32 d2, sorted position) pairs cached pe
 // clearly below the band is a neighbour, every entry clearly above is not, and only the band
 // entries are re-evaluated in sequential f64 (sklearn's arithmetic).  rk2 and the neighbour
 // sets are therefore exactly those of the all-f64 algorithm (kept as the overflow fallback).
+//
+// This general kernel handles any neighbourhood; in the batched path it only sees the points the
+// fast kernel below deferred (`queue` = their sorted positions, `queue_cnt` per scan).
 __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
     const float4* __restrict__ sorted_all, const int* __restrict__ cells_all, const GridMeta* __restrict__ meta,
     const int64_t* __restrict__ off, int G, int k_nn, double r2_max, KnnLevels lv,
     double* __restrict__ rk2_all, int32_t* __restrict__ knn_all, int32_t* __restrict__ knn_cnt_all,
-    int32_t* __restrict__ flags) {
+    int32_t* __restrict__ flags, const int32_t* __restrict__ queue_all, const int32_t* __restrict__ queue_cnt) {
   const int s = blockIdx.y;
   const GridMeta m = meta[s];
-  const int n = m.n;
+  const int n = queue_all ? queue_cnt[s] : m.n;
+  const int32_t* __restrict__ queue = queue_all ? queue_all + off[s] : nullptr;
   const float4* __restrict__ sorted = sorted_all + off[s];
   const int* __restrict__ cells = cells_all + (size_t)s * cell_stride(G);
   __shared__ int hist_sh[kKnnWarps][kBins];
@@ -263,7 +267,8 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
   const int warps_per_grid = gridDim.x * kKnnWarps;
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
 
-  for (int pos = blockIdx.x * kKnnWarps + wib; pos < n; pos += warps_per_grid) {
+  for (int item = blockIdx.x * kKnnWarps + wib; item < n; item += warps_per_grid) {
+    const int pos = queue ? queue[item] : item;
     const float4 p = sorted[pos];
     const int i = __float_as_int(p.w);
     const int cx = cell_coord(p.x, m.x0, m.inv_cell), cy = cell_coord(p.y, m.y0, m.inv_cell);
@@ -395,6 +400,250 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
       break;
     }
     if (lane == 0) {
+      if (emitted > k_nn) { atomicOr(flags, 2); emitted = k_nn; }   // ties beyond k: list truncated
+      rk2_all[off[s] + i] = rk2;
+      knn_cnt_all[off[s] + i] = emitted;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- H.1b: the common case, tuned for occupancy ---------------------------------------------------
+// Same algorithm as knn_select_kernel for neighbourhoods that fit its compact scratch: list
+// entries are (f32 d2, u16 {window row, offset in the row}) and the histogram packs two 16-bit
+// counters per word, 6.5 KB per warp instead of 9, and the all-f64 fallback lives in the general
+// kernel, which keeps this one at 64 registers: 8 CTAs per SM instead of 6.  Points whose
+// window has a row of more than 4095 points, or more than kListCap candidates inside the radius,
+// are appended to `queue` for the general kernel.
+constexpr int kRowBits = 12;
+
+__device__ __forceinline__ int bin_of_f(float d2, float lo, float scale) {
+  const int b = (int)((d2 - lo) * scale);
+  return b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
+}
+
+// k-th smallest (1-based `k_nn`) of the cnt >= k_nn floats in ld2 (all <= R2).  Entry e belongs to
+// lane e % 32; bit e / 32 of the lane's `alive` word says whether it passed every closed level of
+// the nested 256-bin histograms, so a pass evaluates at most the previous and the open level.
+__device__ __forceinline__ float kth_in_list(const float* ld2, int cnt, int k_nn, float R2, unsigned* hist32, int lane,
+                                             int32_t* flags) {
+  const int nchunks = (cnt + 31) >> 5;
+  unsigned alive = 0u;
+  for (int c = 0; c < nchunks; ++c) alive |= (unsigned)(c * 32 + lane < cnt) << c;
+  float lo = 0.f, scale = (float)kBins / (R2 * (float)(1.0 + 1e-6) + 1e-30f);
+  float lo_prev = 0.f, scale_prev = 0.f;
+  int sel_prev = -1;
+  int need = k_nn;
+  for (int round = 0; round < kMaxDepth; ++round) {
+#pragma unroll
+    for (int j = 0; j < kBins / 64; ++j) hist32[lane + 32 * j] = 0u;
+    __syncwarp();
+    for (int c = 0; c < nchunks; ++c) {
+      if (!((alive >> c) & 1u)) continue;
+      const float d2 = ld2[c * 32 + lane];
+      if (sel_prev >= 0 && bin_of_f(d2, lo_prev, scale_prev) != sel_prev) { alive &= ~(1u << c); continue; }
+      const int b = bin_of_f(d2, lo, scale);
+      atomicAdd(&hist32[b >> 1], 1u << ((b & 1) * 16));
+    }
+    __syncwarp();
+    int loc[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned w = hist32[lane * 4 + j];
+      loc[2 * j] = (int)(w & 0xffffu); loc[2 * j + 1] = (int)(w >> 16);
+      tot += loc[2 * j] + loc[2 * j + 1];
+    }
+    int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    int exc = inc - tot, selbin = -1, below = 0, inbin = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (selbin < 0 && exc + loc[j] >= need && need > exc) { selbin = lane * 8 + j; below = exc; inbin = loc[j]; }
+      exc += loc[j];
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, selbin >= 0);
+    const int src = __ffs(who) - 1;
+    selbin = __shfl_sync(0xffffffffu, selbin, src);
+    below = __shfl_sync(0xffffffffu, below, src);
+    inbin = __shfl_sync(0xffffffffu, inbin, src);
+    need -= below;
+    if (inbin <= 32 || round == kMaxDepth - 1) {
+      float mine = __int_as_float(0x7f800000);
+      int have = 0;
+      for (int c = 0; c < nchunks; ++c) {                      // warp-uniform trip count
+        const float d2 = ((alive >> c) & 1u) ? ld2[c * 32 + lane] : 0.f;
+        const bool in = ((alive >> c) & 1u) && bin_of_f(d2, lo, scale) == selbin;
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const int slot = have + __popc(bal & ((1u << lane) - 1u));
+        for (unsigned rem = bal; rem; rem &= rem - 1) {
+          const int srcl = __ffs(rem) - 1;
+          const int dst = __shfl_sync(0xffffffffu, slot, srcl);
+          const float v = __shfl_sync(0xffffffffu, d2, srcl);
+          if (lane == dst) mine = v;
+        }
+        have += __popc(bal);
+      }
+      if (inbin > 32 && lane == 0) atomicOr(flags, 1);          // unresolved tie block
+      if (have == 1) return __shfl_sync(0xffffffffu, mine, 0);
+      int rank = 0;
+      for (int l2 = 0; l2 < 32; ++l2) {
+        const float v = __shfl_sync(0xffffffffu, mine, l2);
+        rank += (v < mine) || (v == mine && l2 < lane);
+      }
+      const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < have);
+      return __shfl_sync(0xffffffffu, mine, hitl ? __ffs(hitl) - 1 : 0);
+    }
+    lo_prev = lo; scale_prev = scale; sel_prev = selbin;
+    lo = lo + (float)selbin * (1.f / scale);
+    scale = scale * (float)kBins;
+  }
+  return 0.f;     // not reached: the last round always returns
+}
+
+__global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
+    const float4* __restrict__ sorted_all, const int* __restrict__ cells_all, const GridMeta* __restrict__ meta,
+    const int64_t* __restrict__ off, int G, int k_nn, double r2_max, KnnLevels lv,
+    double* __restrict__ rk2_all, int32_t* __restrict__ knn_all, int32_t* __restrict__ knn_cnt_all,
+    int32_t* __restrict__ flags, int32_t* __restrict__ queue_all, int32_t* __restrict__ queue_cnt) {
+  const int s = blockIdx.y;
+  const GridMeta m = meta[s];
+  const int n = m.n;
+  const float4* __restrict__ sorted = sorted_all + off[s];
+  const int* __restrict__ cells = cells_all + (size_t)s * cell_stride(G);
+  int32_t* __restrict__ queue = queue_all + off[s];
+  __shared__ unsigned hist_sh[kKnnWarps][kBins / 2];
+  __shared__ float list_d2[kKnnWarps][kListCap];
+  __shared__ unsigned short list_pos[kKnnWarps][kListCap];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned* hist32 = hist_sh[wib];
+  float* ld2 = list_d2[wib];
+  unsigned short* lpos = list_pos[wib];
+  const int warps_per_grid = gridDim.x * kKnnWarps;
+  const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+
+  for (int pos = blockIdx.x * kKnnWarps + wib; pos < n; pos += warps_per_grid) {
+    const float4 p = sorted[pos];
+    const int i = __float_as_int(p.w);
+    const int cx = cell_coord(p.x, m.x0, m.inv_cell), cy = cell_coord(p.y, m.y0, m.inv_cell);
+    double rk2 = kInf;
+    int32_t* out = knn_all + ((size_t)off[s] + i) * k_nn;
+    int emitted = 0;
+    bool defer = false;
+    for (int level = 0; level < lv.n; ++level) {
+      const int L = lv.L[level];
+      const double R2 = lv.r2[level];
+      const bool last = level == lv.n - 1;
+      const int xa = clampi(cx - L, 0, G - 1), xb = clampi(cx + L, 0, G - 1);
+      const int ya = clampi(cy - L, 0, G - 1), yb = clampi(cy + L, 0, G - 1);
+      const int nrows = yb - ya + 1;                           // <= 31 (checked by the launcher)
+      int rkb = 0, rlen = 0;                                   // lane r: position range of window row r
+      if (lane < nrows) {
+        rkb = __ldg(cells + (ya + lane) * G + xa);
+        rlen = __ldg(cells + (ya + lane) * G + xb + 1) - rkb;
+      }
+      if (!last && warp_sum(rlen) <= lv.min_pop) continue;     // too few points for a fine level
+      if (__any_sync(0xffffffffu, rlen >= (1 << kRowBits))) { defer = true; break; }
+      const float eps = 4e-6f * (float)R2 + 1e-9f;             // f32 evaluation error bound, as in the general kernel
+      const float band = 8.0f * eps;
+      const float R2f_list = (float)R2 + band;
+      auto position = [&](unsigned short e) { return __shfl_sync(0xffffffffu, rkb, e >> kRowBits) + (int)(e & ((1u << kRowBits) - 1u)); };
+      // ---- pass A: cache (d2, row|offset) of everything that could be within R2; count the sure ones ----
+      int cnt = 0, sure = 0;
+      for (int r = 0; r < nrows; ++r) {
+        const int kb = __shfl_sync(0xffffffffu, rkb, r), len = __shfl_sync(0xffffffffu, rlen, r);
+        for (int o0 = 0; o0 < len; o0 += 32) {
+          const int o = o0 + lane;
+          float d2 = 0.f;
+          bool in = false;
+          if (o < len && kb + o != pos) {
+            const float4 q = __ldg(sorted + kb + o);
+            const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+            d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            in = d2 <= R2f_list;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, in);
+          const int slot = cnt + __popc(bal & lt);
+          if (in && slot < kListCap) { ld2[slot] = d2; lpos[slot] = (unsigned short)((r << kRowBits) | o); }
+          cnt += __popc(bal);
+          sure += __popc(__ballot_sync(0xffffffffu, in && d2 < (float)R2 - band));
+        }
+      }
+      __syncwarp();
+      if (cnt > kListCap) { defer = true; break; }
+      auto exact_d2 = [&](int kpos) {
+        const float4 q = __ldg(sorted + kpos);
+        return sqdist_f64_seq(p.x, p.y, p.z, q.x, q.y, q.z);
+      };
+      double cut = r2_max;              // exact cut-off for emission
+      // fine level: only when k points are certainly inside the fine radius (the window then
+      // provably holds the k nearest); radius level: whenever k candidates are cached
+      if (sure >= k_nn || (last && cnt >= k_nn)) {
+        const float v32 = kth_in_list(ld2, cnt, k_nn, R2f_list, hist32, lane, flags);
+        int n_low = 0, n_band = 0;
+        double mine = kInf;
+        for (int e0 = 0; e0 < cnt; e0 += 32) {
+          const int e = e0 + lane;
+          const bool live = e < cnt;
+          const float d2 = live ? ld2[e] : 0.f;
+          const unsigned short code = live ? lpos[e] : (unsigned short)0;
+          const int kpos = position(code);
+          const bool low = live && d2 < v32 - band;
+          const bool inb = live && !low && d2 <= v32 + band;
+          n_low += __popc(__ballot_sync(0xffffffffu, low));
+          const unsigned bal = __ballot_sync(0xffffffffu, inb);
+          const int slot = n_band + __popc(bal & lt);
+          const double ex = inb ? exact_d2(kpos) : 0.0;
+          for (unsigned rem = bal; rem; rem &= rem - 1) {
+            const int srcl = __ffs(rem) - 1;
+            const int dst = __shfl_sync(0xffffffffu, slot, srcl);
+            const double vv = __shfl_sync(0xffffffffu, ex, srcl);
+            if (lane == dst) mine = vv;
+          }
+          n_band += __popc(bal);
+        }
+        if (n_band > 32) { if (lane == 0) atomicOr(flags, 1); }
+        const int need = k_nn - n_low;                     // 1-based rank inside the band
+        int rank = 0;
+        if (n_band > 1)
+          for (int l2 = 0; l2 < 32; ++l2) {
+            const double vv = __shfl_sync(0xffffffffu, mine, l2);
+            rank += (vv < mine) || (vv == mine && l2 < lane);
+          }
+        const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < min(n_band, 32));
+        if (hitl) rk2 = __shfl_sync(0xffffffffu, mine, __ffs(hitl) - 1);
+        else if (lane == 0) atomicOr(flags, 1);
+        cut = fmin(rk2, r2_max);
+      } else if (!last) {
+        continue;      // (also the borderline case: the radius level, whose window contains this one, decides)
+      }
+      // ---- emission from the list: sure-below, sure-above, or exact inside the band around cut ----
+      const float cutf = (float)cut;
+      for (int e0 = 0; e0 < cnt; e0 += 32) {
+        const int e = e0 + lane;
+        const bool live = e < cnt;
+        const float d2 = live ? ld2[e] : 0.f;
+        const unsigned short code = live ? lpos[e] : (unsigned short)0;
+        const int kpos = position(code);
+        bool in = false;
+        if (live) {
+          if (d2 < cutf - band) in = true;
+          else if (d2 <= cutf + band) in = exact_d2(kpos) <= cut;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const int slot = emitted + __popc(bal & lt);
+        if (in && slot < k_nn) out[slot] = __float_as_int(__ldg(sorted + kpos).w);
+        emitted += __popc(bal);
+      }
+      break;
+    }
+    if (defer) {                                               // warp-uniform
+      if (lane == 0) queue[atomicAdd(&queue_cnt[s], 1)] = pos;
+    } else if (lane == 0) {
       if (emitted > k_nn) { atomicOr(flags, 2); emitted = k_nn; }   // ties beyond k: list truncated
       rk2_all[off[s] + i] = rk2;
       knn_cnt_all[off[s] + i] = emitted;
@@ -738,6 +987,8 @@ extern "C" size_t modest_graph_workspace_bytes(int n_scans, int64_t n_points_tot
   add(sizeof(double) * (size_t)n_points_total);                    // rk2
   add(sizeof(int32_t) * (size_t)n_points_total * n_neighbors);     // knn
   add(sizeof(int32_t) * (size_t)n_points_total);                   // knn_cnt
+  add(sizeof(int32_t) * (size_t)n_points_total);                   // points deferred to the general kNN kernel
+  add(sizeof(int32_t) * (size_t)n_scans);                          // ... and their number per scan
   return b + 256;
 }
 
@@ -764,6 +1015,8 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
   double* rk2 = ar.take<double>(n_points_total);
   int32_t* knn = ar.take<int32_t>((size_t)n_points_total * n_neighbors);
   int32_t* knn_cnt = ar.take<int32_t>(n_points_total);
+  int32_t* queue = ar.take<int32_t>(n_points_total);
+  int32_t* queue_cnt = ar.take<int32_t>(n_scans);
   MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
 
   const float cell = kGraphCell * kGraphSlack;
@@ -800,8 +1053,13 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
   if (wblocks < 1) wblocks = 1;
   if (wblocks > 148 * 16) wblocks = 148 * 16;
   MODEST_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t), stream));
-  knn_select_kernel<<<dim3(wblocks, n_scans), kKnnWarps * 32, 0, stream>>>(sorted, cells, meta, d_off, G, n_neighbors, r2_max,
-                                                               lv, rk2, knn, knn_cnt, d_flags);
+  MODEST_CUDA(cudaMemsetAsync(queue_cnt, 0, sizeof(int32_t) * (size_t)n_scans, stream));
+  knn_select_fast_kernel<<<dim3(wblocks, n_scans), kKnnWarps * 32, 0, stream>>>(sorted, cells, meta, d_off, G, n_neighbors, r2_max,
+                                                                    lv, rk2, knn, knn_cnt, d_flags, queue, queue_cnt);
+  MODEST_LAUNCH_CHECK("knn_select_fast_kernel");
+  // the deferred points (dense neighbourhoods; normally a few per mille): a narrow grid, it idles when the queues are empty
+  knn_select_kernel<<<dim3(64, n_scans), kKnnWarps * 32, 0, stream>>>(sorted, cells, meta, d_off, G, n_neighbors, r2_max, lv, rk2,
+                                                                    knn, knn_cnt, d_flags, queue, queue_cnt);
   MODEST_LAUNCH_CHECK("knn_select_kernel");
   int mblocks = (int)((max_points * 32 + 255) / 256);
   if (mblocks < 1) mblocks = 1;
@@ -810,7 +1068,7 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
                                                                  d_n_kept, n_neighbors, rk2, knn, knn_cnt, d_nbr,
                                                                  d_nbr_w, d_nbr_cnt, partition_eps, d_nbr_eps_cnt);
   MODEST_LAUNCH_CHECK("mutual_edges_kernel");
-  note_launch(2);
+  note_launch(3);
   return MODEST_OK;
 }
 
