@@ -584,8 +584,13 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
       // provably holds the k nearest); radius level: whenever k candidates are cached
       if (sure >= k_nn || (last && cnt >= k_nn)) {
         const float v32 = kth_in_list(ld2, cnt, k_nn, R2f_list, hist32, lane, flags);
+        // When the k-th distance lies clearly inside the graph radius, everything clearly below
+        // it is a neighbour and is emitted in this same pass; the few entries inside the band
+        // around it are kept in registers, ranked exactly, and emitted right after.
+        const bool fused = v32 + band < (float)r2_max - band;           // warp-uniform
         int n_low = 0, n_band = 0;
         double mine = kInf;
+        int mine_pos = 0;
         for (int e0 = 0; e0 < cnt; e0 += 32) {
           const int e = e0 + lane;
           const bool live = e < cnt;
@@ -594,7 +599,13 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
           const int kpos = position(code);
           const bool low = live && d2 < v32 - band;
           const bool inb = live && !low && d2 <= v32 + band;
-          n_low += __popc(__ballot_sync(0xffffffffu, low));
+          const unsigned bal_low = __ballot_sync(0xffffffffu, low);
+          n_low += __popc(bal_low);
+          if (fused) {
+            const int slot = emitted + __popc(bal_low & lt);
+            if (low && slot < k_nn) out[slot] = __float_as_int(__ldg(sorted + kpos).w);
+            emitted += __popc(bal_low);
+          }
           const unsigned bal = __ballot_sync(0xffffffffu, inb);
           const int slot = n_band + __popc(bal & lt);
           const double ex = inb ? exact_d2(kpos) : 0.0;
@@ -602,7 +613,8 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
             const int srcl = __ffs(rem) - 1;
             const int dst = __shfl_sync(0xffffffffu, slot, srcl);
             const double vv = __shfl_sync(0xffffffffu, ex, srcl);
-            if (lane == dst) mine = vv;
+            const int pp_ = __shfl_sync(0xffffffffu, kpos, srcl);
+            if (lane == dst) { mine = vv; mine_pos = pp_; }
           }
           n_band += __popc(bal);
         }
@@ -618,6 +630,14 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
         if (hitl) rk2 = __shfl_sync(0xffffffffu, mine, __ffs(hitl) - 1);
         else if (lane == 0) atomicOr(flags, 1);
         cut = fmin(rk2, r2_max);
+        if (fused) {
+          const bool in = lane < min(n_band, 32) && mine <= cut;
+          const unsigned bal = __ballot_sync(0xffffffffu, in);
+          const int slot = emitted + __popc(bal & lt);
+          if (in && slot < k_nn) out[slot] = __float_as_int(__ldg(sorted + mine_pos).w);
+          emitted += __popc(bal);
+          break;
+        }
       } else if (!last) {
         continue;      // (also the borderline case: the radius level, whose window contains this one, decides)
       }
