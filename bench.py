@@ -166,7 +166,7 @@ def run_ours(args):
     scan_batch = pl.make_batch(ptc_host, [torch.zeros(N_POINTS) for _ in cases], calibs)
     scan_batch.pp = pp_out
 
-    # two independent pipelines on two streams: consecutive steps alternate between them so that
+    # independent pipelines on their own streams: consecutive steps alternate between them so that
     # the many one-CTA-per-scan kernels of one step overlap the wide kernels of the other
     lanes = [(torch.cuda.Stream(), pp_mod.PPScorer(), pl.SeedLabelPipeline(),
               torch.empty(pp_batch.n_query_total, dtype=torch.float32, device="cuda")) for _ in range(args.streams)]
@@ -311,7 +311,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scans-per-step", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=2, help="independent pipeline lanes for the device-resident loop")
+    ap.add_argument("--streams", type=int, default=3, help="independent pipeline lanes for the device-resident loop")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
