@@ -415,6 +415,28 @@ def test_edge_cases_empty_ragged_and_degenerate():
     assert np.array_equal(single.labels.cpu().numpy(), lab[:5000])
 
 
+def test_graph_dense_neighbourhoods_take_the_general_knn_kernel():
+    """Neighbourhoods beyond the fast kNN kernel's scratch (a window row of > 4095 points, more
+    than 1024 candidates inside the radius) are queued for the general kernel and its all-f64
+    path; the graph still equals scikit-learn's edge for edge."""
+    from modest_b200.generate_cluster_mask.utils import clustering_utils as cu
+    from oracle import modest_oracle as orc
+    rng = np.random.default_rng(5)
+    ball = rng.normal(0, 1, (1500, 3))
+    ball = ball / np.linalg.norm(ball, axis=1, keepdims=True) * rng.uniform(0, 0.25, (1500, 1)) + [12.0, 3.0, 0.5]
+    cube = rng.uniform(0, 0.3, (5000, 3)) + [25.0, -6.0, 0.0]
+    ring = np.column_stack([rng.uniform(5, 40, 1200), rng.uniform(-15, 15, 1200), rng.uniform(-1, 2, 1200)])
+    ptc = np.concatenate([ball, cube, ring]).astype(np.float32)
+    ptc = ptc[rng.permutation(len(ptc))]
+    pp = rng.uniform(0, 1, len(ptc)).astype(np.float32)
+    G = cu.precompute_affinity_matrix(ptc, pp, neighbor_type="radius_mutual_knn", affinity_type="l1",
+                                      n_neighbors=70, radius=2.)
+    Go = orc.affinity_graph(ptc, pp)
+    Go.sort_indices()
+    assert G.shape == Go.shape and np.array_equal(G.indptr, Go.indptr) and np.array_equal(G.indices, Go.indices)
+    assert np.array_equal(G.data, Go.data)
+
+
 def test_iou_and_nms_edge_cases():
     from modest_b200.generate_cluster_mask.utils.iou3d_nms import iou3d_nms_utils as ours
     e = torch.zeros((0, 7), device="cuda")
