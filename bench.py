@@ -192,10 +192,13 @@ def run_ours(args):
         """The public streaming API: pinned host batches in, label text out; H2D of batch k+1
         overlaps the kernels of batch k and the text formatting of batch k-1."""
         n_lines = 0
-        for ids, texts in engine.process(host_batch for _ in range(n_steps)):
+        blobs = {}
+        for k, (ids, texts) in enumerate(engine.process(host_batch for _ in range(n_steps))):
             if world > 1:
-                dist.gather_blobs({i: t.encode() for i, t in zip(ids, texts)})
+                blobs.update({k * world * B + i: t.encode() for i, t in zip(ids, texts)})   # scan ids are rank * B + s
             n_lines += sum(t.count("\n") + 1 for t in texts if t)
+        if world > 1:       # the path's one collective: label files collated on rank 0 once per run
+            dist.gather_blobs(blobs)
         d2h_bytes[0] = engine.d2h_bytes_last
         return n_lines
 
