@@ -190,6 +190,8 @@ int modest_ground_mask_batch(const float* d_ptc, int point_stride, const int64_t
  *                 with (double)w <= partition_eps first and d_nbr_eps_cnt (NP) i32 receives their
  *                 number (-1 for rows left unpartitioned).  The order of the entries of a row
  *                 carries no other meaning (the reference's CSR is rebuilt sorted by column).
+ *                 With partitioned rows d_nbr_w may be NULL: only the eps-edges are then written
+ *                 (rows of d_nbr_eps_cnt entries) -- all DBSCAN needs (n_neighbors <= 96).
  * ------------------------------------------------------------------------------------------ */
 size_t modest_graph_workspace_bytes(int n_scans, int64_t n_points_total, int n_neighbors,
                                     int grid_dim);

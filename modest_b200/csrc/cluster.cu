@@ -730,8 +730,11 @@ __global__ void __launch_bounds__(256) mutual_edges_kernel(
         const unsigned me = 1u << lane;
         int slot = -1;
         if (bal_e[t] & me) slot = have_e + __popc(bal_e[t] & lt);
-        else if (bal_o[t] & me) slot = have_o + __popc(bal_o[t] & lt);
-        if (slot >= 0) { orow[slot] = jj[t]; wrow[slot] = ww[t]; }
+        else if ((bal_o[t] & me) && nbr_w) slot = have_o + __popc(bal_o[t] & lt);   // no weights wanted: eps-edges only
+        if (slot >= 0) {
+          orow[slot] = jj[t];
+          if (nbr_w) wrow[slot] = ww[t];
+        }
         have_e += __popc(bal_e[t]);
         have_o += __popc(bal_o[t]);
       }
@@ -770,7 +773,7 @@ __global__ void __launch_bounds__(256) dbscan_core_kernel(
     int deg = 1;                                   // the point itself (sklearn adds the diagonal)
     const int pre = eps_cnt ? eps_cnt[base + i] : -1;
     if (pre >= 0) deg += pre;                      // rows partitioned by mutual_edges_kernel
-    else {
+    else if (nbr_w) {
       const int m = nbr_cnt[base + i];
       const float* w = nbr_w + (size_t)(base + i) * k_nn;
       for (int c = 0; c < m; ++c) deg += ((double)w[c] <= eps);
@@ -821,7 +824,7 @@ __global__ void __launch_bounds__(256) dbscan_init_kernel(
     int best = i;
     for (int c = lane; c < m; c += 32) {
       const int j = nbr[row + c];
-      if (j < best && (pre >= 0 || (double)nbr_w[row + c] <= eps) && core[base + j]) best = j;
+      if (j < best && (pre >= 0 || (nbr_w && (double)nbr_w[row + c] <= eps)) && core[base + j]) best = j;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -864,7 +867,7 @@ __global__ void __launch_bounds__(256) dbscan_union_kernel(
     const int pi = parent[base + i];
     for (int c = lane; c < m; c += 32) {
       const int j = nbr[row + c];
-      if (j < i && (pre >= 0 || (double)nbr_w[row + c] <= eps) && core[base + j] && parent[base + j] != pi)
+      if (j < i && (pre >= 0 || (nbr_w && (double)nbr_w[row + c] <= eps)) && core[base + j] && parent[base + j] != pi)
         uf_union(parent + base, i, j);
     }
   }
@@ -948,7 +951,7 @@ __global__ void __launch_bounds__(256) dbscan_label_borders_kernel(
       const size_t row = (size_t)(base + i) * k_nn;
       for (int c = 0; c < m; ++c) {
         const int j = nbr[row + c];
-        if ((pre >= 0 || (double)nbr_w[row + c] <= eps) && core[base + j]) lab = min(lab, labels_kept[base + j]);
+        if ((pre >= 0 || (nbr_w && (double)nbr_w[row + c] <= eps)) && core[base + j]) lab = min(lab, labels_kept[base + j]);
       }
       if (lab == 0x7fffffff) lab = -1;
       border_lab[base + i] = lab;       // labels_kept of cores is still being read by other threads
@@ -1020,8 +1023,12 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scans <= 0 || n_points_total <= 0) return MODEST_OK;
   if (grid_dim <= 0) grid_dim = 288;
-  MODEST_REQUIRE(d_kept && d_off && d_n_kept && d_nbr && d_nbr_w && d_nbr_cnt && d_flags && d_ws,
+  MODEST_REQUIRE(d_kept && d_off && d_n_kept && d_nbr && d_nbr_cnt && d_flags && d_ws,
                  "affinity_graph: null pointer argument");
+  // without a weights buffer only the eps-edges are produced, which needs the partitioned rows
+  MODEST_REQUIRE(d_nbr_w || (d_nbr_eps_cnt && partition_eps >= 0.0 && n_neighbors <= 32 * kMutualChunks),
+                 "affinity_graph: d_nbr_w may only be NULL together with partition_eps >= 0, d_nbr_eps_cnt and n_neighbors <= %d",
+                 32 * kMutualChunks);
   MODEST_REQUIRE(n_neighbors >= 1 && n_neighbors <= 1024, "affinity_graph: n_neighbors %d out of range", n_neighbors);
   MODEST_REQUIRE(radius > 0.0 && radius <= 64.0, "affinity_graph: radius %g out of range", radius);
   MODEST_REQUIRE(ws_bytes >= modest_graph_workspace_bytes(n_scans, n_points_total, n_neighbors, grid_dim),
@@ -1103,7 +1110,7 @@ extern "C" int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept
                                    int32_t* d_n_clusters, void* d_ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scans <= 0 || n_points_total <= 0) return MODEST_OK;
-  MODEST_REQUIRE(d_off && d_n_kept && d_kept_idx && d_nbr && d_nbr_w && d_nbr_cnt && d_labels_kept &&
+  MODEST_REQUIRE(d_off && d_n_kept && d_kept_idx && d_nbr && (d_nbr_w || d_nbr_eps_cnt) && d_nbr_cnt && d_labels_kept &&
                      d_labels_full && d_n_clusters && d_ws, "dbscan: null pointer argument");
   MODEST_REQUIRE(ws_bytes >= modest_dbscan_workspace_bytes(n_points_total), "dbscan: workspace too small");
   MODEST_REQUIRE(n_scans <= 65535, "dbscan: more than 65535 scans in one launch");

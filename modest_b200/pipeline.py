@@ -247,14 +247,17 @@ class SeedLabelPipeline:
         return kept, kept_idx, n_kept, mask
 
     # ------------------------------------------------------------------ stage H
-    def affinity_graph(self, kept, off, n_kept, n_scans, n_points, max_points, stream=None, partition_eps=None):
+    def affinity_graph(self, kept, off, n_kept, n_scans, n_points, max_points, stream=None, partition_eps=None,
+                       eps_edges_only=False):
         """Returns nbr, nbr_w, nbr_cnt, flags.  With `partition_eps` (the DBSCAN radius the caller
-        will use) every row lists its eps-edges first and `self.nbr_eps_cnt` holds their number."""
+        will use) every row lists its eps-edges first and `self.nbr_eps_cnt` holds their number;
+        with `eps_edges_only` nothing else is written (nbr_w is None): all DBSCAN needs."""
         dev = kept.device
         g = self.cfg["graph"]
         k = int(g["n_neighbors"])
+        eps_edges_only = bool(eps_edges_only and partition_eps is not None and k <= 96)
         nbr = self._scr.get("nbr", n_points * k, torch.int32, dev)
-        nbr_w = self._scr.get("nbr_w", n_points * k, torch.float32, dev)
+        nbr_w = None if eps_edges_only else self._scr.get("nbr_w", n_points * k, torch.float32, dev)
         nbr_cnt = self._scr.get("nbr_cnt", n_points, torch.int32, dev)
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
         self.nbr_eps_cnt = self._scr.get("nbr_eps_cnt", n_points, torch.int32, dev) if partition_eps is not None else None
@@ -341,7 +344,8 @@ class SeedLabelPipeline:
             b, r.plane, pe["offset"], pe["range"], cfg["limit_range"], want_mask=want_debug, stream=stream)
         eps = float(cfg["clustering"]["DBSCAN"]["eps"])
         nbr, nbr_w, nbr_cnt, gflags = self.affinity_graph(kept, b.off, r.n_kept, b.n_scans, b.n_points,
-                                                          b.max_points, stream=stream, partition_eps=eps)
+                                                          b.max_points, stream=stream, partition_eps=eps,
+                                                          eps_edges_only=not want_debug)
         _, r.labels_raw, r.n_clusters = self.dbscan(b.off, r.n_kept, r.kept_idx, b.n_scans, b.n_points,
                                                     b.max_points, nbr, nbr_w, nbr_cnt, stream=stream,
                                                     nbr_eps_cnt=self.nbr_eps_cnt)

@@ -107,6 +107,18 @@ def test_eps_partitioned_rows_give_the_same_graph_and_labels(golden_case, name):
                                           nbr_eps_cnt=p.nbr_eps_cnt)
     assert np.array_equal(labels_full.cpu().numpy(), g["labels_raw"])
     assert int(n_clusters.cpu()[0]) == g["labels_raw"].max() + 1
+    # what the fused path runs: eps-edges only, no weights buffer at all
+    nbr.fill_(-7)
+    nbr, no_w, nbr_cnt, _ = p.affinity_graph(kept, b.off, n_kept, 1, b.n_points, b.max_points, partition_eps=eps,
+                                             eps_edges_only=True)
+    assert no_w is None and np.array_equal(p.nbr_eps_cnt.cpu().numpy()[:nk], pre)
+    c_idx = nbr.cpu().numpy()[:nk * k].reshape(nk, k)
+    head = slot < pre[:, None]
+    assert np.array_equal(np.sort(np.where(head, c_idx, big), axis=1), np.sort(np.where(head, b_idx, big), axis=1))
+    _, labels_full, n_clusters = p.dbscan(b.off, n_kept, kept_idx, 1, b.n_points, b.max_points, nbr, None, nbr_cnt,
+                                          nbr_eps_cnt=p.nbr_eps_cnt)
+    assert np.array_equal(labels_full.cpu().numpy(), g["labels_raw"])
+    assert int(n_clusters.cpu()[0]) == g["labels_raw"].max() + 1
 
 
 @pytest.mark.parametrize("name", CASES)
