@@ -235,8 +235,31 @@ def run_ours(args):
     clocks = sampler.stop()
     buf = (ctypes.c_float * 256)()
     n_prof = lib.modest_pp_profile_read(buf, 256)
-    pp_ms = float(np.mean([buf[i] for i in range(n_prof)])) if n_prof else float("nan")
+    pp_ms_overlapped = float(np.mean([buf[i] for i in range(n_prof)])) if n_prof else float("nan")
+    # The roofline kernel on its own: in the loop above its launches share the SMs with the other
+    # lanes' kernels, which stretches every launch.  The same steps once more on ONE lane give
+    # the kernel's own duration and a step it can be compared with (what the ncu launch list of
+    # `--streams 1` shows as well); both durations are reported.
+    k_single = min(args.steps, 8)
+    assert lib.modest_pp_profile_enable(k_single) == 0
+    lanes_all, lanes[:] = list(lanes), lanes[:1]
+    device_step(0)
+    barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(main_stream)
+    lanes[0][0].wait_event(ev2)
+    for k in range(k_single):
+        device_step(200 + k)
+    e = torch.cuda.Event()
+    e.record(lanes[0][0])
+    main_stream.wait_event(e)
+    ev3.record(main_stream)
+    barrier()
+    ms_single = ev2.elapsed_time(ev3) / k_single
+    n_prof = lib.modest_pp_profile_read(buf, 256)
+    pp_ms = float(np.mean([buf[i] for i in range(min(n_prof, k_single))])) if n_prof else float("nan")
     lib.modest_pp_profile_enable(0)
+    lanes[:] = lanes_all
     n_boxes = int(res.n_boxes.sum().item())
 
     # ---- e2e (host buffers in, label text out)
@@ -259,9 +282,9 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
 
     if world > 1:
-        t = torch.tensor([ms, e2e_s * 1e3, pp_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_s * 1e3, pp_ms, ms_single, pp_ms_overlapped], dtype=torch.float64, device="cuda")
         td.all_reduce(t, op=td.ReduceOp.MAX)
-        ms, e2e_s, pp_ms = float(t[0]), float(t[1]) / 1e3, float(t[2])
+        ms, e2e_s, pp_ms, ms_single, pp_ms_overlapped = float(t[0]), float(t[1]) / 1e3, float(t[2]), float(t[3]), float(t[4])
     if world > 1:
         td.barrier()
         td.destroy_process_group()
@@ -292,7 +315,10 @@ def run_ours(args):
                                        "scaled to this launch's scan count",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": pp_ms,
-                     "share_of_step": pp_ms / (ms / args.steps)},
+                     "share_of_step": pp_ms / ms_single,
+                     "timed_on": f"{k_single} single-lane steps after the throughput loop ({ms_single:.3f} ms per step); "
+                                 "in the overlapped loop the same launch lasts kernel_ms_overlapped",
+                     "kernel_ms_overlapped": pp_ms_overlapped},
     }
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
     if world == 1 and not args.no_cpu_baseline:
