@@ -145,6 +145,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    numa_cpus = dist.bind_to_gpu_numa(local)      # before any pinned allocation (first touch decides the node)
     if world > 1:
         dist.init("nccl")
     lib = _lib.lib()
@@ -276,10 +277,12 @@ def run_ours(args):
     del probe, probe_d
     e2e_run(max(args.warmup, 6))          # every slot of the engine's ring is touched before timing
     barrier()
+    engine.host_s.update(upload=0.0, launch=0.0, wait=0.0, text=0.0, batches=0)
     t0 = time.perf_counter()
     e2e_run(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    host_ms = {k: round(1e3 * v / max(engine.host_s["batches"], 1), 2) for k, v in engine.host_s.items() if k != "batches"}
 
     if world > 1:
         t = torch.tensor([ms, e2e_s * 1e3, pp_ms, ms_single, pp_ms_overlapped], dtype=torch.float64, device="cuda")
@@ -303,11 +306,14 @@ def run_ours(args):
                    "ransac": "device-drawn minimal sets, 100 trials scored, sklearn accept/early-stop replay",
                    "l2": f"inputs larger than L2: {h2d_bytes / 1e6:.0f} MB touched per step",
                    "streams": args.streams,
+                   "host_cpus": (f"{len(numa_cpus)} CPUs of the GPU's NUMA node" if numa_cpus else
+                                 f"{len(os.sched_getaffinity(0))} (no NUMA binding: topology not exposed or already local)"),
                    "boxes_last_step": n_boxes},
         "clocks": clocks,
         "e2e": {"value": total_scans / e2e_s, "unit": "scans/s", "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": int(d2h_bytes[0]), "h2d_link_gbs_measured": round(h2d_gbs, 1),
-                "h2d_gbs_used": round(h2d_bytes * args.steps / e2e_s / 1e9, 1)},
+                "h2d_gbs_used": round(h2d_bytes * args.steps / e2e_s / 1e9, 1),
+                "host_ms_per_batch": host_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "pp_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": int(PP_COUNT_DRAM_TRAFFIC_PER_SCAN * B),

@@ -44,6 +44,39 @@ def init(backend=None):
     td.init_process_group(backend=backend)
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(device_index=None, sysfs="/sys/bus/pci/devices"):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned staging
+    buffers allocated afterwards (first touch) are local to that GPU's PCIe root: a staging buffer
+    on the other socket halves or thirds the host->device rate of the streaming engine.  Returns
+    the CPU set chosen, or None when the topology is not exposed (then nothing is changed)."""
+    try:
+        if not torch.cuda.is_available() or not hasattr(os, "sched_setaffinity"):
+            return None
+        idx = torch.cuda.current_device() if device_index is None else int(device_index)
+        pr = torch.cuda.get_device_properties(idx)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        with open(os.path.join(sysfs, bdf, "local_cpulist")) as fh:
+            local = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0)
+        chosen = local & allowed
+        if not chosen or chosen == allowed:
+            return None
+        os.sched_setaffinity(0, chosen)
+        return chosen
+    except (OSError, AttributeError, ValueError):
+        return None
+
+
 def shard(items, world=None, r=None):
     world = world_size() if world is None else world
     r = rank() if r is None else r
