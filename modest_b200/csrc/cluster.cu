@@ -554,24 +554,43 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
       auto position = [&](unsigned short e) { return __shfl_sync(0xffffffffu, rkb, e >> kRowBits) + (int)(e & ((1u << kRowBits) - 1u)); };
       // ---- pass A: cache (d2, row|offset) of everything that could be within R2; count the sure ones ----
       int cnt = 0, sure = 0;
-      for (int r = 0; r < nrows; ++r) {
-        const int kb = __shfl_sync(0xffffffffu, rkb, r), len = __shfl_sync(0xffffffffu, rlen, r);
-        for (int o0 = 0; o0 < len; o0 += 32) {
-          const int o = o0 + lane;
+      {
+        // the rows' position ranges concatenated: every trip has 32 live lanes but the last
+        // (rows hold ~19 points here, so row-by-row trips run half empty)
+        int incl = rlen;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += u;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - rlen;
+        int row = 0;                                            // of this lane's flat index; only ever advances
+        for (int f0 = 0; f0 < total; f0 += 32) {
+          const int idx = f0 + lane;
+          while (true) {
+            const int end = __shfl_sync(0xffffffffu, incl, row);
+            const bool adv = idx >= end && row < nrows - 1;
+            if (!__any_sync(0xffffffffu, adv)) break;
+            if (adv) ++row;
+          }
+          const int o = idx - __shfl_sync(0xffffffffu, excl, row);
+          const int kq = __shfl_sync(0xffffffffu, rkb, row) + o;
           float d2 = 0.f;
           bool in = false;
-          if (o < len && kb + o != pos) {
-            const float4 q = __ldg(sorted + kb + o);
+          if (idx < total && kq != pos) {
+            const float4 q = __ldg(sorted + kq);
             const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
             d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             in = d2 <= R2f_list;
           }
           const unsigned bal = __ballot_sync(0xffffffffu, in);
           const int slot = cnt + __popc(bal & lt);
-          if (in && slot < kListCap) { ld2[slot] = d2; lpos[slot] = (unsigned short)((r << kRowBits) | o); }
+          if (in && slot < kListCap) { ld2[slot] = d2; lpos[slot] = (unsigned short)((row << kRowBits) | o); }
           cnt += __popc(bal);
-          sure += __popc(__ballot_sync(0xffffffffu, in && d2 < (float)R2 - band));
+          sure += (in && d2 < (float)R2 - band) ? 1 : 0;         // per lane; summed once below
         }
+        sure = __reduce_add_sync(0xffffffffu, sure);
       }
       __syncwarp();
       if (cnt > kListCap) { defer = true; break; }
