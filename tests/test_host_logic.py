@@ -162,3 +162,12 @@ def test_two_rank_gloo_sharding_and_gather(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_numa_binding_helper_is_a_noop_without_topology(tmp_path):
+    """dist.bind_to_gpu_numa only narrows the CPU set when sysfs exposes one for the GPU; its
+    cpulist parser follows the kernel's "a-b,c" grammar."""
+    from modest_b200 import dist
+    assert dist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert dist._parse_cpulist("") == set()
+    assert dist.bind_to_gpu_numa(0, sysfs=str(tmp_path)) is None     # no GPU here / no such device directory
