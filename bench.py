@@ -76,6 +76,23 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_info():
+    """CPU model and library versions of the box the CPU numbers were taken on."""
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.lower().startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    import scipy
+    import sklearn
+    return {"cpu_model": model, "cpu_count": os.cpu_count(), "numpy": np.__version__, "scipy": scipy.__version__,
+            "sklearn": sklearn.__version__}
+
+
 def make_pool(n_scans, seed0):
     from modest_b200 import synth
     return [synth.make_scan_case(seed0 + i, synth.LYFT, n_traversals=N_TRAV, frames_per_traversal=1,
@@ -127,7 +144,8 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": WORKLOAD, "scans_per_step": workers},
             "cpu_baseline": {"value": value, "unit": "scans/s", "cores": workers, "kind": "port",
-                             "sample": f"{workers} scans per step, one per process (cKDTree + sklearn, 1 thread each)"},
+                             "sample": f"{workers} scans per step, one per process (cKDTree + sklearn, 1 thread each)",
+                             "host": host_info()},
             "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -334,7 +352,8 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "scans/s", "cores": 1 if (os.cpu_count() or 1) == 1 else os.cpu_count(),
                                 "kind": "port",
                                 "sample": "1 scan of the same workload, one process: cKDTree single-threaded, "
-                                          "sklearn graph/DBSCAN with n_jobs=-1 as the reference calls them"}
+                                          "sklearn graph/DBSCAN with n_jobs=-1 as the reference calls them",
+                                "host": host_info()}
     print(json.dumps(line))
 
 
