@@ -63,3 +63,39 @@ def test_ransac_restatement_matches_sklearn():
         assert r["n_trials"] == model.n_trials_
         assert (r["inlier_mask"] != model.inlier_mask_).sum() <= 2
         assert np.allclose(r["coef"], model.estimator_.coef_, atol=1e-6)
+
+
+def test_ball_count_restatement_matches_ckdtree():
+    """cKDTree's p=2 ball query == sequential f64 d2 <= r*r on f32-originated coordinates,
+    including points planted a few ulps either side of the sphere surface."""
+    from oracle import modest_oracle as orc
+    rng = np.random.default_rng(11)
+    q = rng.uniform(-3, 3, (400, 3)).astype(np.float32)
+    hist = [rng.uniform(-3, 3, (m, 3)).astype(np.float32) for m in (0, 1, 700, 1500)]
+    d = rng.normal(0, 1, (400, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    shell = np.float32(0.3) * (1 + rng.integers(-4, 5, (400, 1)) * 2.0 ** -22)
+    hist.append((q.astype(np.float64) + d * shell).astype(np.float32))          # hits and misses by a hair
+    assert np.array_equal(orc.neighbor_counts_bruteforce(q, hist), orc.neighbor_counts(q, hist))
+
+
+def test_graph_and_dbscan_restatements_match_sklearn():
+    """mutual-kNN AND radius edge set from first principles == the three sklearn graph calls the
+    reference multiplies; union-find DBSCAN == sklearn.cluster.DBSCAN(metric='precomputed')."""
+    from oracle import modest_oracle as orc
+    rng = np.random.default_rng(12)
+    blobs = [rng.normal(c, 0.4, (120, 3)) for c in ((0, 0, 0), (3, 0.5, 0), (0.5, 4, 0.3))]
+    ptc = np.concatenate(blobs + [rng.uniform(-4, 8, (90, 3))]).astype(np.float32)
+    pp = np.concatenate([rng.normal(m, 0.04, 120) for m in (0.2, 0.5, 0.8)] + [rng.uniform(0, 1, 90)]).astype(np.float32)
+    for k, radius in ((70, 2.0), (10, 0.8)):
+        G = orc.affinity_graph(ptc, pp, n_neighbors=k, radius=radius).tocsr()
+        G.sort_indices()
+        adj, w = orc.affinity_edges_bruteforce(ptc, pp, n_neighbors=k, radius=radius)
+        rows = np.repeat(np.arange(G.shape[0]), np.diff(G.indptr))
+        stored = np.zeros(adj.shape, dtype=bool)
+        stored[rows, G.indices] = True                                # stored entries, whatever their weight
+        assert np.array_equal(stored, adj)
+        assert np.array_equal(G.data, w[rows, G.indices].astype(np.float64))
+        for eps, ms in ((0.1, 10), (0.05, 4)):
+            assert np.array_equal(orc.dbscan_restated(G.indptr, G.indices, G.data, eps, ms),
+                                  orc.dbscan_labels(G, eps, ms))
