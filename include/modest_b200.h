@@ -37,7 +37,7 @@ extern "C" {
 #define MODEST_ERR_CUDA (-2)      /* a CUDA runtime call or launch failed */
 #define MODEST_ERR_CAPACITY (-3)  /* a fixed-capacity device buffer overflowed */
 
-#define MODEST_ABI_VERSION 1
+#define MODEST_ABI_VERSION 2
 
 int modest_abi_version(void);
 const char* modest_last_error(void);
@@ -117,7 +117,11 @@ int modest_pp_profile_read(float* h_ms, int max_out);
  *   consensus set and emits the plane [a,b,c,d] (c > 0) of pointcloud_utils.py:53-62.
  *     d_triples  (n_scans,max_trials,3) i32 indices into each scan's candidate list -- drawn by
  *                the caller (parity: numpy's global RandomState, like sklearn) -- or NULL to
- *                draw them on the device from `seed` (throughput mode)
+ *                draw them on the device (throughput mode): trial h of scan s uses a
+ *                counter-based hash of (seed, d_scan_keys[s], h), so a scan's minimal sets --
+ *                and with them its labels -- do not depend on its slot in the batch or on how
+ *                the scans are sharded over GPUs
+ *     d_scan_keys (n_scans) i64 per-scan key (the scan id) or NULL (key = s)
  *     d_plane    (n_scans,4) f64 out (NaN when no valid consensus set exists)
  *     d_model    (n_scans,3) f64 out or NULL: the float32 coef_[0], coef_[1], intercept_
  *     d_info     (n_scans,4) i32 out: n_candidates, n_trials_ consumed, best trial, n_inliers
@@ -131,8 +135,8 @@ int modest_plane_candidates_batch(const float* d_ptc, int point_stride, const in
 size_t modest_ransac_workspace_bytes(int n_scans, int max_trials);
 int modest_ransac_fit_batch(const float* d_cand, const int64_t* d_off, const int32_t* d_n_cand,
                             const float* d_thr, int n_scans, int64_t max_points,
-                            const int32_t* d_triples, uint64_t seed, int max_trials,
-                            double* d_plane, double* d_model, int32_t* d_info,
+                            const int32_t* d_triples, uint64_t seed, const int64_t* d_scan_keys,
+                            int max_trials, double* d_plane, double* d_model, int32_t* d_info,
                             int32_t* d_triples_out, uint8_t* d_inlier_mask, void* d_ws,
                             size_t ws_bytes, void* stream);
 

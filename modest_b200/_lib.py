@@ -36,7 +36,7 @@ SIGNATURES = {
     "modest_plane_candidates_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _f32, _f32, _f32, _f32, _f32,
                                                 _vp, _vp, _vp, _vp]),
     "modest_ransac_workspace_bytes": (_sz, [C.c_int, C.c_int]),
-    "modest_ransac_fit_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _i64, _vp, C.c_uint64, C.c_int,
+    "modest_ransac_fit_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _i64, _vp, C.c_uint64, _vp, C.c_int,
                                           _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "modest_road_candidates_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _f64, _f64, _vp, _vp, _vp, _vp]),
     "modest_road_plane_fit_batch": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _i64, _vp, C.c_uint64, C.c_int, _vp, _vp, _vp,

@@ -100,6 +100,11 @@ __global__ void __launch_bounds__(1024) ground_mask_compact_kernel(
 // ---- H.1: k-th neighbour distance and candidate lists, one warp per point ---------------------
 constexpr int kBins = 256;
 constexpr int kMaxDepth = 6;
+// More than k points at or inside the k-th neighbour distance (exact ties, e.g. duplicate or
+// zero-filled returns): the row keeps the first k in window order, like a k-nearest query that
+// breaks ties by traversal order, and is marked so that the mutual test looks the partner up in
+// the row instead of trusting the distance alone (the mutual graph must stay symmetric).
+constexpr int kTruncatedRow = 1 << 30;
 
 template <typename T>
 struct BinChain {            // nested linear binning of d2: level l keeps bin sel[l] of [lo[l], lo[l]+256/scale[l])
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
       break;
     }
     if (lane == 0) {
-      if (emitted > k_nn) { atomicOr(flags, 2); emitted = k_nn; }   // ties beyond k: list truncated
+      if (emitted > k_nn) { atomicOr(flags, 2); emitted = k_nn | kTruncatedRow; }   // ties beyond k: first k kept
       rk2_all[off[s] + i] = rk2;
       knn_cnt_all[off[s] + i] = emitted;
     }
@@ -683,7 +688,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
     if (defer) {                                               // warp-uniform
       if (lane == 0) queue[atomicAdd(&queue_cnt[s], 1)] = pos;
     } else if (lane == 0) {
-      if (emitted > k_nn) { atomicOr(flags, 2); emitted = k_nn; }   // ties beyond k: list truncated
+      if (emitted > k_nn) { atomicOr(flags, 2); emitted = k_nn | kTruncatedRow; }   // ties beyond k: first k kept
       rk2_all[off[s] + i] = rk2;
       knn_cnt_all[off[s] + i] = emitted;
     }
@@ -713,7 +718,7 @@ __global__ void __launch_bounds__(256) mutual_edges_kernel(
   const bool partition = nbr_eps_cnt != nullptr && eps_first >= 0.0 && k_nn <= 32 * kMutualChunks;
   for (int i = warp; i < n; i += nwarps) {
     const float4 p = kept[base + i];
-    const int m = knn_cnt[base + i];
+    const int m = knn_cnt[base + i] & ~kTruncatedRow;
     const int32_t* row = knn + (size_t)(base + i) * k_nn;
     int32_t* orow = nbr + (size_t)(base + i) * k_nn;
     float* wrow = nbr_w + (size_t)(base + i) * k_nn;
@@ -724,7 +729,14 @@ __global__ void __launch_bounds__(256) mutual_edges_kernel(
       const float4 q = kept[base + j];
       const double d2 = sqdist_f64_seq(q.x, q.y, q.z, p.x, p.y, p.z);   // same expression as row j used
       w = fabsf(__fsub_rn(p.w, q.w));
-      return d2 <= rk2[base + j];
+      if (d2 > rk2[base + j]) return false;
+      if (knn_cnt[base + j] & kTruncatedRow) {              // row j kept k of its tied neighbours: is i one of them?
+        const int32_t* rj = knn + (size_t)(base + j) * k_nn;
+        bool found = false;
+        for (int t = 0; t < k_nn; ++t) found |= rj[t] == i;
+        return found;
+      }
+      return true;
     };
     if (partition) {
       int jj[kMutualChunks];

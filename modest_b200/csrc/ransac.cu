@@ -157,8 +157,8 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 template <typename T>
 __global__ void ransac_hypotheses_kernel(
     const T* __restrict__ cand, const int64_t* __restrict__ off, const int32_t* __restrict__ n_cand,
-    const int32_t* __restrict__ triples, uint64_t seed, int H, HypT<T>* __restrict__ hyps,
-    int32_t* __restrict__ triples_out) {
+    const int32_t* __restrict__ triples, uint64_t seed, const int64_t* __restrict__ scan_keys, int H,
+    HypT<T>* __restrict__ hyps, int32_t* __restrict__ triples_out) {
   const int s = blockIdx.x;
   const int n = n_cand[s];
   const T* p = cand + 3 * off[s];
@@ -170,8 +170,10 @@ __global__ void ransac_hypotheses_kernel(
       if (triples) {
         for (int k = 0; k < 3; ++k) id[k] = triples[((size_t)s * H + h) * 3 + k];
         ok = id[0] >= 0 && id[1] >= 0 && id[2] >= 0 && id[0] < n && id[1] < n && id[2] < n;
-      } else {   // device generator: three distinct indices from a counter-based hash
-        uint64_t ctr = splitmix64(seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(s + 1))) + (uint64_t)h * 64u;
+      } else {   // device generator: three distinct indices from a counter-based hash of
+                 // (seed, scan key, trial) -- a scan's draws do not depend on its batch slot
+        const uint64_t key = scan_keys ? (uint64_t)scan_keys[s] : (uint64_t)s;
+        uint64_t ctr = splitmix64(seed ^ (0xD1B54A32D192ED03ull * (key + 1))) + (uint64_t)h * 64u;
         int got = 0;
         for (int it = 0; it < 64 && got < 3; ++it) {
           const uint64_t r = splitmix64(ctr + it);
@@ -452,16 +454,16 @@ __global__ void __launch_bounds__(1024) road_candidates_kernel(
 
 template <typename T>
 static int ransac_fit_impl(const T* d_cand, const int64_t* d_off, const int32_t* d_n_cand, const T* d_thr, int n_scans,
-                           int64_t max_points, const int32_t* d_triples, uint64_t seed, int max_trials, double* d_plane,
-                           double* d_model, int32_t* d_info, int32_t* d_triples_out, uint8_t* d_inlier_mask, void* d_ws,
+                           int64_t max_points, const int32_t* d_triples, uint64_t seed, const int64_t* d_scan_keys,
+                           int max_trials, double* d_plane, double* d_model, int32_t* d_info, int32_t* d_triples_out, uint8_t* d_inlier_mask, void* d_ws,
                            size_t ws_bytes, cudaStream_t stream, int mode) {
   Arena ar(d_ws, ws_bytes);
   HypT<T>* hyps = ar.take<HypT<T>>((size_t)n_scans * max_trials);
   HypStat* stats = ar.take<HypStat>((size_t)n_scans * max_trials);
   MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
   MODEST_CUDA(cudaMemsetAsync(stats, 0, sizeof(HypStat) * (size_t)n_scans * max_trials, stream));
-  ransac_hypotheses_kernel<T><<<n_scans, 128, 0, stream>>>(d_cand, d_off, d_n_cand, d_triples, seed, max_trials, hyps,
-                                                          d_triples_out);
+  ransac_hypotheses_kernel<T><<<n_scans, 128, 0, stream>>>(d_cand, d_off, d_n_cand, d_triples, seed, d_scan_keys, max_trials,
+                                                          hyps, d_triples_out);
   MODEST_LAUNCH_CHECK("ransac_hypotheses_kernel");
   const int chunk = 256 * kPtsPerThread;
   dim3 grid((unsigned)((max_points + chunk - 1) / chunk), n_scans);
@@ -515,15 +517,15 @@ static int fit_args_ok(const void* d_cand, const void* d_off, const void* d_n_ca
 
 extern "C" int modest_ransac_fit_batch(const float* d_cand, const int64_t* d_off, const int32_t* d_n_cand,
                                        const float* d_thr, int n_scans, int64_t max_points,
-                                       const int32_t* d_triples, uint64_t seed, int max_trials,
-                                       double* d_plane, double* d_model, int32_t* d_info,
+                                       const int32_t* d_triples, uint64_t seed, const int64_t* d_scan_keys,
+                                       int max_trials, double* d_plane, double* d_model, int32_t* d_info,
                                        int32_t* d_triples_out, uint8_t* d_inlier_mask, void* d_ws,
                                        size_t ws_bytes, void* stream_) {
   if (n_scans <= 0) return MODEST_OK;
   const int rc = fit_args_ok(d_cand, d_off, d_n_cand, d_thr, d_plane, d_info, d_ws, n_scans, max_trials, ws_bytes);
   if (rc != MODEST_OK) return rc;
-  return ransac_fit_impl<float>(d_cand, d_off, d_n_cand, d_thr, n_scans, max_points, d_triples, seed, max_trials, d_plane,
-                                d_model, d_info, d_triples_out, d_inlier_mask, d_ws, ws_bytes,
+  return ransac_fit_impl<float>(d_cand, d_off, d_n_cand, d_thr, n_scans, max_points, d_triples, seed, d_scan_keys, max_trials,
+                                d_plane, d_model, d_info, d_triples_out, d_inlier_mask, d_ws, ws_bytes,
                                 static_cast<cudaStream_t>(stream_), 0);
 }
 
@@ -552,7 +554,7 @@ extern "C" int modest_road_plane_fit_batch(const double* d_cand, const int64_t* 
   if (n_scans <= 0) return MODEST_OK;
   const int rc = fit_args_ok(d_cand, d_off, d_n_cand, d_thr, d_plane, d_info, d_ws, n_scans, max_trials, ws_bytes);
   if (rc != MODEST_OK) return rc;
-  return ransac_fit_impl<double>(d_cand, d_off, d_n_cand, d_thr, n_scans, max_points, d_triples, seed, max_trials,
+  return ransac_fit_impl<double>(d_cand, d_off, d_n_cand, d_thr, n_scans, max_points, d_triples, seed, nullptr, max_trials,
                                  d_plane, nullptr, d_info, nullptr, nullptr, d_ws, ws_bytes,
                                  static_cast<cudaStream_t>(stream_), 1);
 }

@@ -144,12 +144,16 @@ class SeedLabelEngine:
             small_h.copy_(torch.from_numpy(small))
             trav_h.copy_(torch.from_numpy(trav_off))
             calib_h.copy_(torch.from_numpy(crow))
+            keys_h = slot.pinned("keys_h", (len(hb.scan_ids),), torch.int64)
+            keys_h.copy_(torch.tensor([pl.scan_key(i) for i in hb.scan_ids], dtype=torch.int64))
             small_d = slot.buf("off", small.shape, torch.int64)
             trav_d = slot.buf("trav", trav_off.shape, torch.int32)
             calib_d = slot.buf("calib", crow.shape, torch.float64)
             small_d.copy_(small_h, non_blocking=True)
             trav_d.copy_(trav_h, non_blocking=True)
             calib_d.copy_(calib_h, non_blocking=True)
+            keys_d = slot.buf("keys", (len(hb.scan_ids),), torch.int64)
+            keys_d.copy_(keys_h, non_blocking=True)
             q = slot.buf("q", hb.query_xyz.shape, torch.float32)
             h = slot.buf("h", hb.hist_xyz.shape, torch.float32)
             p = slot.buf("p", hb.ptc.shape, torch.float32)
@@ -164,7 +168,7 @@ class SeedLabelEngine:
             pp = slot.buf("pp", (int(q_off[-1]),), torch.float32)
             slot.scan_batch = pl.ScanBatch(ptc=p, off=small_d[:a], pp=pp, calib=calib_d,
                                            P2=tb["P2"], h_off=q_off,
-                                           scan_ids=hb.scan_ids)
+                                           scan_ids=hb.scan_ids, scan_keys=keys_d)
             slot.host = hb
             slot.ready.record(self.copy_stream)
 
@@ -173,7 +177,9 @@ class SeedLabelEngine:
         with torch.cuda.stream(slot.stream):
             slot.stream.wait_event(slot.ready)
             slot.scorer(slot.pp_batch, out=slot.scan_batch.pp, stream=slot.stream)
-            slot.result = slot.pipe.run(slot.scan_batch, rng="device", seed=self.seed + step, stream=slot.stream)
+            # one seed for the whole run: the draws of a scan are keyed by its id, not by the
+            # step or the batch slot, so batching and sharding do not change its labels
+            slot.result = slot.pipe.run(slot.scan_batch, rng="device", seed=self.seed, stream=slot.stream)
             r = slot.result
             # small results to pinned host memory, still on the compute stream
             r.h_boxes = slot.pinned("h_boxes", r.boxes.shape, torch.float64)
@@ -182,6 +188,11 @@ class SeedLabelEngine:
             r.h_boxes.copy_(r.boxes, non_blocking=True)
             r.h_n.copy_(r.n_boxes, non_blocking=True)
             r.h_keep.copy_(r.keep, non_blocking=True)
+            # capacity / tie flags of the fixed-size device buffers travel with the boxes: a batch
+            # whose cluster or box tables overflowed must not be turned into label text silently
+            r.h_flags = slot.pinned("h_flags", (2,), torch.int32)
+            r.h_flags[0:1].copy_(r.flags["graph"], non_blocking=True)
+            r.h_flags[1:2].copy_(r.flags["fit"], non_blocking=True)
             slot.done.record(slot.stream)
 
     # ---- stage 3: label text on the host ----------------------------------------------------------
@@ -190,8 +201,9 @@ class SeedLabelEngine:
         slot.done.synchronize()
         t1 = time.perf_counter()
         r, b = slot.result, slot.scan_batch
+        self.pipe.check_flag_values(int(r.h_flags[0]), int(r.h_flags[1]))
         hb_, hn, hk = r.h_boxes.numpy(), r.h_n.numpy(), r.h_keep.numpy()
-        self.d2h_bytes_last = hb_.nbytes + hn.nbytes + hk.nbytes
+        self.d2h_bytes_last = hb_.nbytes + hn.nbytes + hk.nbytes + 8
         texts = self.pipe.format_labels_batch(hb_, hn, hk, b.P2)
         self.host_s["wait"] += t1 - t0
         self.host_s["text"] += time.perf_counter() - t1

@@ -68,6 +68,7 @@ class ScanBatch:
     P2: np.ndarray               # (S,3,4) f64 host
     h_off: np.ndarray            # host copy of off
     scan_ids: list = field(default_factory=list)
+    scan_keys: torch.Tensor = None   # (S) i64 cuda: per-scan key of the device RANSAC draws (the scan id)
 
     @property
     def n_scans(self):
@@ -96,6 +97,16 @@ def calib_P2(calib) -> np.ndarray:
     return np.asarray(P, np.float64).reshape(3, 4)
 
 
+def scan_key(scan_id) -> int:
+    """i64 key of a scan for the device RANSAC draws: the integer scan id ("000123" -> 123);
+    any other identifier is hashed (stable across runs and ranks)."""
+    try:
+        return int(scan_id) & (2**63 - 1)
+    except (TypeError, ValueError):
+        import zlib
+        return zlib.crc32(str(scan_id).encode())
+
+
 def make_batch(ptcs, pps, calibs, scan_ids=None, device="cuda") -> ScanBatch:
     sizes = [int(p.shape[0]) for p in ptcs]
     h_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
@@ -109,9 +120,10 @@ def make_batch(ptcs, pps, calibs, scan_ids=None, device="cuda") -> ScanBatch:
         torch.zeros((0,), device=device)
     crow = np.stack([calib_row(c) for c in calibs]) if calibs else np.zeros((0, 21))
     P2 = np.stack([calib_P2(c) for c in calibs]) if calibs else np.zeros((0, 3, 4))
+    ids = list(scan_ids) if scan_ids is not None else list(range(len(ptcs)))
     return ScanBatch(ptc=ptc, off=torch.from_numpy(h_off).to(device), pp=pp,
-                     calib=torch.from_numpy(crow).to(device), P2=P2, h_off=h_off,
-                     scan_ids=list(scan_ids) if scan_ids is not None else list(range(len(ptcs))))
+                     calib=torch.from_numpy(crow).to(device), P2=P2, h_off=h_off, scan_ids=ids,
+                     scan_keys=torch.tensor([scan_key(i) for i in ids], dtype=torch.int64).to(device))
 
 
 @dataclass
@@ -120,6 +132,8 @@ class BatchResult:
     plane2: torch.Tensor = None          # (S,4) f64
     ransac_info: torch.Tensor = None     # (S,4) i32 (first fit)
     ransac_info2: torch.Tensor = None
+    triples: torch.Tensor = None         # (S,100,3) i32 minimal sets of the first / second fit (want_debug)
+    triples2: torch.Tensor = None
     n_kept: torch.Tensor = None          # (S) i32
     kept_idx: torch.Tensor = None        # (NP) i32
     mask: torch.Tensor = None            # (NP) u8 final_mask
@@ -188,7 +202,8 @@ class SeedLabelPipeline:
                    return_debug=False):
         """estimate_plane() for every scan of the batch.
 
-        rng="device": minimal sets drawn on the GPU from `seed` (no host sync).
+        rng="device": minimal sets drawn on the GPU from (`seed`, b.scan_keys[s], trial) -- no host
+                      sync, and a scan's draws do not depend on its slot in the batch.
         rng="numpy":  minimal sets taken from numpy's global RandomState exactly as sklearn
                       would; scans are processed in order, the stream advances by n_trials_ draws
                       per scan (two host syncs for the whole batch when `seed` is a list of
@@ -221,7 +236,8 @@ class SeedLabelPipeline:
         tri_out = torch.empty((S, MAX_TRIALS, 3), dtype=torch.int32, device=dev) if return_debug else None
         _lib.check(self.lib.modest_ransac_fit_batch(
             _lib.ptr(cand), _lib.ptr(b.off), _lib.ptr(n_cand), _lib.ptr(thr), S, b.max_points,
-            _lib.ptr(triples), C.c_uint64(int(seed) & (2**64 - 1)), MAX_TRIALS, _lib.ptr(plane), _lib.ptr(model),
+            _lib.ptr(triples), C.c_uint64(int(seed) & (2**64 - 1)), _lib.ptr(b.scan_keys), MAX_TRIALS, _lib.ptr(plane),
+            _lib.ptr(model),
             _lib.ptr(info), _lib.ptr(tri_out), _lib.ptr(inl), _lib.ptr(ws), ws.numel(), sp), "modest_ransac_fit_batch")
         if rng == "numpy":
             h_info = info.cpu().numpy()
@@ -339,7 +355,12 @@ class SeedLabelPipeline:
         cfg = self.cfg
         pe = cfg["plane_estimate"]
         r = BatchResult()
-        r.plane, r.ransac_info = self.fit_planes(b, pe["max_hs"], pe["range"], rng=rng, seed=seed, stream=stream)
+        if want_debug:     # also hand back the minimal sets that were used (tests replay them in sklearn)
+            r.plane, r.ransac_info, dbg = self.fit_planes(b, pe["max_hs"], pe["range"], rng=rng, seed=seed,
+                                                          stream=stream, return_debug=True)
+            r.triples = dbg["triples"].clone()
+        else:
+            r.plane, r.ransac_info = self.fit_planes(b, pe["max_hs"], pe["range"], rng=rng, seed=seed, stream=stream)
         kept, r.kept_idx, r.n_kept, r.mask = self.ground_masks(
             b, r.plane, pe["offset"], pe["range"], cfg["limit_range"], want_mask=want_debug, stream=stream)
         eps = float(cfg["clustering"]["DBSCAN"]["eps"])
@@ -349,8 +370,13 @@ class SeedLabelPipeline:
         _, r.labels_raw, r.n_clusters = self.dbscan(b.off, r.n_kept, r.kept_idx, b.n_scans, b.n_points,
                                                     b.max_points, nbr, nbr_w, nbr_cnt, stream=stream,
                                                     nbr_eps_cnt=self.nbr_eps_cnt)
-        r.plane2, r.ransac_info2 = self.fit_planes(b, FILTER_PLANE["max_hs"], FILTER_PLANE["range"], rng=rng,
-                                                   seed=seed + 0x9E3779B9, stream=stream)
+        if want_debug:
+            r.plane2, r.ransac_info2, dbg = self.fit_planes(b, FILTER_PLANE["max_hs"], FILTER_PLANE["range"], rng=rng,
+                                                            seed=seed + 0x9E3779B9, stream=stream, return_debug=True)
+            r.triples2 = dbg["triples"].clone()
+        else:
+            r.plane2, r.ransac_info2 = self.fit_planes(b, FILTER_PLANE["max_hs"], FILTER_PLANE["range"], rng=rng,
+                                                       seed=seed + 0x9E3779B9, stream=stream)
         r.labels_filtered, r.labels, r.boxes, r.n_boxes, _, fflags = self.filter_and_fit(
             b, r.labels_raw, r.n_clusters, r.plane2, stream=stream)
         if cfg["nms"]["enable"]:
@@ -364,19 +390,20 @@ class SeedLabelPipeline:
     def check_flags(result: "BatchResult"):
         """Raise when a fixed-capacity device buffer overflowed (results would be silently
         truncated); warn about distance ties the reference resolves by traversal order."""
-        g = int(result.flags["graph"].item())
-        f = int(result.flags["fit"].item())
+        SeedLabelPipeline.check_flag_values(int(result.flags["graph"].item()), int(result.flags["fit"].item()))
+
+    @staticmethod
+    def check_flag_values(g: int, f: int):
         if f & 4:
             raise RuntimeError("more DBSCAN clusters than max_clusters: rebuild the pipeline with a larger capacity")
         if f & 16:
             raise RuntimeError("more boxes than max_boxes: rebuild the pipeline with a larger capacity")
-        if g & 2:
-            raise RuntimeError("a point has more than n_neighbors equidistant k-th neighbours (duplicate points?)")
         if f & 8:
             raise ValueError("a fitted box contains no scan point (the reference raises on ys.max() of an empty array)")
-        if g & 1:
+        if g & 3:
             import warnings
-            warnings.warn("kNN distance ties: neighbour sets may differ from scikit-learn's traversal order")
+            warnings.warn("kNN distance ties" + (" beyond n_neighbors (duplicate points?)" if g & 2 else "") +
+                          ": neighbour sets may differ from scikit-learn's traversal order")
 
     # ------------------------------------------------------------------ stage O (host)
     def label_texts(self, b: ScanBatch, boxes, n_boxes, keep):

@@ -120,12 +120,47 @@ def _plane_from_linear_model(coef, intercept):
     return -np.array([w[0] / nrm, w[1] / nrm, w[2] / nrm, intercept / nrm])
 
 
-def fit_ground_plane(xyz, max_hs=-1.5, ptc_range=((-20, 70), (-20, 20)), return_model=False):
+class injected_minimal_sets:
+    """Context manager: while active, sklearn's RANSAC trial loop (_ransac.py:485-487) takes its
+    minimal sets from `triples` ((n,3) indices into the candidate list, consumed in order)
+    instead of drawing them from numpy's global RandomState.  The reference never seeds that
+    stream, so ANY sequence of draws is a valid run of it; this is how the
+    tests check the GPU's throughput mode (device-drawn minimal sets) against the unmodified
+    library: same draws in, same n_trials_ / consensus set / labels out.  `used` counts draws."""
+
+    def __init__(self, triples):
+        self.triples = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+        self.used = 0
+
+    def _draw(self, n_population, n_samples, random_state=None, method="auto"):
+        assert n_samples == 3 and self.used < len(self.triples), "injected minimal sets exhausted"
+        t = self.triples[self.used]
+        assert t.min() >= 0 and t.max() < n_population
+        self.used += 1
+        return t.copy()
+
+    def __enter__(self):
+        import sklearn.linear_model._ransac as mod
+        self._mod, self._orig = mod, mod.sample_without_replacement
+        mod.sample_without_replacement = self._draw
+        return self
+
+    def __exit__(self, *exc):
+        self._mod.sample_without_replacement = self._orig
+        return False
+
+
+def fit_ground_plane(xyz, max_hs=-1.5, ptc_range=((-20, 70), (-20, 20)), return_model=False, draws=None):
     """utils/pointcloud_utils.py:44-65 with it=1 -- sklearn RANSACRegressor() defaults on
-    (x,y)->z of the candidate points; consumes the *global* numpy RNG like the reference."""
+    (x,y)->z of the candidate points; consumes the *global* numpy RNG like the reference
+    (or, for the tests of the device-drawn mode, the minimal sets in `draws`)."""
     from sklearn.linear_model import RANSACRegressor
     sel = xyz[plane_candidates_mask(xyz, max_hs, ptc_range)]
-    model = RANSACRegressor().fit(sel[:, [0, 1]], sel[:, 2])
+    if draws is not None:
+        with injected_minimal_sets(draws):
+            model = RANSACRegressor().fit(sel[:, [0, 1]], sel[:, 2])
+    else:
+        model = RANSACRegressor().fit(sel[:, [0, 1]], sel[:, 2])
     plane = _plane_from_linear_model(model.estimator_.coef_, model.estimator_.intercept_)
     return (plane, model) if return_model else plane
 
@@ -378,12 +413,15 @@ def cluster_is_valid(xyz, pp, plane, min_points=10, max_volume=40, min_volume=0.
     return not (np.percentile(pp, percentile) > min_percentile_pp_score)
 
 
-def filter_cluster_labels(ptc, pp, labels, **gates):
+def filter_cluster_labels(ptc, pp, labels, plane_draws=None, info=None, **gates):
     """utils/clustering_utils.py:119-135 -- a SECOND RANSAC plane with hard-coded
     max_hs=-1.5 / range ((-70,70),(-50,50)), invalid clusters -> -1, then ids are
     re-numbered by sorted(set(labels)) (so noise becomes 0 when any noise exists)."""
     out = labels.copy()
-    plane = fit_ground_plane(ptc, max_hs=-1.5, ptc_range=((-70, 70), (-50, 50)))
+    plane, model = fit_ground_plane(ptc, max_hs=-1.5, ptc_range=((-70, 70), (-50, 50)), draws=plane_draws,
+                                    return_model=True)
+    if info is not None:
+        info["n_trials2"] = int(model.n_trials_)
     for cid in range(out.max() + 1):
         member = out == cid
         if not cluster_is_valid(ptc[member, :3], pp[member], plane, **gates):
@@ -728,14 +766,17 @@ DEFAULT_MASK_CFG = dict(
 )
 
 
-def seed_mask_for_scan(ptc, pp, calib, cfg=None, seed=None, return_stages=False):
+def seed_mask_for_scan(ptc, pp, calib, cfg=None, seed=None, return_stages=False, draws=None):
     """generate_mask.py:52-103 for one scan.  `seed` re-seeds the global numpy RNG first (the
-    reference never seeds; SURVEY.md 8(a)-R / 8(d) define seed = 1024 + scan id for parity)."""
+    reference never seeds; SURVEY.md 8(a)-R / 8(d) define seed = 1024 + scan id for parity);
+    `draws` = (minimal sets of the first fit, of filter_labels' fit) replaces the stream."""
     cfg = DEFAULT_MASK_CFG if cfg is None else cfg
     if seed is not None:
         np.random.seed(seed)
     pe = cfg["plane_estimate"]
-    plane = fit_ground_plane(ptc[:, :3], max_hs=pe["max_hs"], ptc_range=pe["range"])
+    plane, model1 = fit_ground_plane(ptc[:, :3], max_hs=pe["max_hs"], ptc_range=pe["range"],
+                                     draws=None if draws is None else draws[0], return_model=True)
+    info = dict(n_trials1=int(model1.n_trials_))
     keep = keep_above_plane(ptc[:, :3], plane, offset=pe["offset"], only_range=pe["range"])
     keep &= limit_range_mask(ptc, cfg["limit_range"])
     g = cfg["graph"]
@@ -743,7 +784,8 @@ def seed_mask_for_scan(ptc, pp, calib, cfg=None, seed=None, return_stages=False)
     db = cfg["clustering"]["DBSCAN"]
     raw = np.full(ptc.shape[0], -1, dtype=np.int64)
     raw[keep] = dbscan_labels(graph, db["eps"], db["min_samples"])
-    labels, plane2 = filter_cluster_labels(ptc, pp, raw, **cfg["filtering"])
+    labels, plane2 = filter_cluster_labels(ptc, pp, raw, plane_draws=None if draws is None else draws[1],
+                                           info=info, **cfg["filtering"])
     rect = calib.velo_to_rect(ptc[:, :3])
     objs = []
     f = cfg["filtering"]
@@ -756,7 +798,7 @@ def seed_mask_for_scan(ptc, pp, calib, cfg=None, seed=None, return_stages=False)
     uniq = np.unique(labels)
     labels = np.searchsorted(uniq, labels).astype(labels.dtype)
     if return_stages:
-        return labels, objs, dict(plane=plane, keep=keep, raw=raw, plane2=plane2, graph=graph)
+        return labels, objs, dict(plane=plane, keep=keep, raw=raw, plane2=plane2, graph=graph, **info)
     return labels, objs
 
 

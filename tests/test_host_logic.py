@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree"
-    assert handle.modest_abi_version() == 1
+    assert handle.modest_abi_version() == 2
 
 
 def test_missing_library_fails_loudly(monkeypatch):
