@@ -81,20 +81,34 @@ int modest_transform_frames_batch(const float* d_in, int point_stride,
  *                d_count_off[s] (i64 element offsets, n_scans+1 entries).  When NULL the counts
  *                live in the workspace only.
  *   d_pp         (NQ) f32 out.
+ *
+ * Two history passes produce the same bits:
+ *   tiled (default)  -- needs the HOST copies of the offset tables (h_q_off, h_h_off, h_trav_off:
+ *                the arrays the caller built before uploading them), at most 32 traversals per
+ *                scan and grid_dim % 8 == 0.  The batch is cut into groups of consecutive scans
+ *                of about `group_points` history points (0 = default 2 M) so that a group's
+ *                intermediate stays L2-resident; `bin_records` float4 slots of the workspace hold
+ *                it: take the value modest_pp_bin_records() returns for the same tables.
+ *   global hash      -- any input; taken when a host table is NULL, bin_records == 0,
+ *                group_points < 0, or a scan has more than 32 traversals.
  * ------------------------------------------------------------------------------------------ */
+int64_t modest_pp_bin_records(const int64_t* h_h_off, const int32_t* h_trav_off, int n_scans,
+                              int64_t group_points);
 size_t modest_pp_workspace_bytes(int n_scans, int64_t n_query_total, int64_t n_count_total,
-                                 int grid_dim);
+                                 int grid_dim, int64_t bin_records);
 int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_q_off,
                           const float* d_hist_xyz, const int64_t* d_h_off,
                           const int32_t* d_trav_off, int n_scans, int n_trav_total,
                           int64_t n_query_total, int64_t n_count_total,
                           int64_t max_query_points, int64_t max_trav_points, double radius,
                           int grid_dim, int32_t* d_counts, const int64_t* d_count_off,
-                          float* d_pp, void* d_ws, size_t ws_bytes, void* stream);
+                          float* d_pp, const int64_t* h_q_off, const int64_t* h_h_off,
+                          const int32_t* h_trav_off, int64_t group_points, int64_t bin_records,
+                          void* d_ws, size_t ws_bytes, void* stream);
 
-/* Timing hook for the dominant kernel (pp_count_kernel): with n_slots > 0 every
- * modest_pp_score_batch call records a CUDA event pair around that kernel on the launching
- * stream, in a ring of n_slots pairs (n_slots = 0 switches it off).  After synchronising the
+/* Timing hook for the history pass (tiled: tile query + per group count / plan / scatter /
+ * join kernels; global hash: pp_count_kernel): with n_slots > 0 every modest_pp_score_batch call
+ * records a CUDA event pair around it on the launching stream, in a ring of n_slots pairs (n_slots = 0 switches it off).  After synchronising the
  * stream, modest_pp_profile_read writes the durations [ms] of the most recent launches
  * (newest first) into h_ms and returns how many it wrote. */
 int modest_pp_profile_enable(int n_slots);

@@ -28,9 +28,11 @@ SIGNATURES = {
     "modest_last_error": (C.c_char_p, []),
     "modest_launch_count": (_i64, []),
     "modest_transform_frames_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp]),
-    "modest_pp_workspace_bytes": (_sz, [C.c_int, _i64, _i64, C.c_int]),
+    "modest_pp_bin_records": (_i64, [_vp, _vp, C.c_int, _i64]),
+    "modest_pp_workspace_bytes": (_sz, [C.c_int, _i64, _i64, C.c_int, _i64]),
     "modest_pp_score_batch": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _i64, _i64, _i64,
-                                        _i64, _f64, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                        _i64, _f64, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64,
+                                        _vp, _sz, _vp]),
     "modest_pp_profile_enable": (C.c_int, [C.c_int]),
     "modest_pp_profile_read": (C.c_int, [_vp, C.c_int]),
     "modest_plane_candidates_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _f32, _f32, _f32, _f32, _f32,

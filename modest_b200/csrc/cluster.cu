@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
         v32 = v;
         int n_low = 0, n_band = 0;
         double mine = kInf;
+        double bmin = kInf, bmax = -kInf;                  // over ALL band entries (tie blocks > 32)
         scan_list([&](bool live, float d2, int kpos) {
           const bool low = live && d2 < v32 - band;
           const bool inb = live && !low && d2 <= v32 + band;
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
           const unsigned bal = __ballot_sync(0xffffffffu, inb);
           const int slot = n_band + __popc(bal & ((1u << lane) - 1u));
           const double ex = inb ? exact_d2(kpos) : 0.0;
+          if (inb) { bmin = fmin(bmin, ex); bmax = fmax(bmax, ex); }
           for (unsigned rem = bal; rem; rem &= rem - 1) {
             const int srcl = __ffs(rem) - 1;
             const int dst = __shfl_sync(0xffffffffu, slot, srcl);
@@ -374,17 +376,26 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
           }
           n_band += __popc(bal);
         });
-        if (n_band > 32) { if (lane == 0) atomicOr(flags, 1); }
         const int need = k_nn - n_low;                     // 1-based rank inside the band
-        int rank = 0;
-        if (n_band > 1)
-          for (int l2 = 0; l2 < 32; ++l2) {
-            const double vv = __shfl_sync(0xffffffffu, mine, l2);
-            rank += (vv < mine) || (vv == mine && l2 < lane);
-          }
-        const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < min(n_band, 32));
-        if (hitl) rk2 = __shfl_sync(0xffffffffu, mine, __ffs(hitl) - 1);
-        else if (lane == 0) atomicOr(flags, 1);
+        bool tie_block = false;                            // > 32 band entries, all exactly equal
+        if (n_band > 32) {
+          bmin = warp_min(bmin); bmax = warp_max(bmax);
+          tie_block = bmin == bmax;
+          if (!tie_block && lane == 0) atomicOr(flags, 1);
+        }
+        if (tie_block) {
+          rk2 = bmin;                                      // every rank inside the block has this value
+        } else {
+          int rank = 0;
+          if (n_band > 1)
+            for (int l2 = 0; l2 < 32; ++l2) {
+              const double vv = __shfl_sync(0xffffffffu, mine, l2);
+              rank += (vv < mine) || (vv == mine && l2 < lane);
+            }
+          const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < min(n_band, 32));
+          if (hitl) rk2 = __shfl_sync(0xffffffffu, mine, __ffs(hitl) - 1);
+          else if (lane == 0) atomicOr(flags, 1);
+        }
         cut = fmin(rk2, r2_max);
       } else if (!last) {
         continue;      // (also the borderline case: the radius level, whose window contains this one, decides)
@@ -614,6 +625,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
         const bool fused = v32 + band < (float)r2_max - band;           // warp-uniform
         int n_low = 0, n_band = 0;
         double mine = kInf;
+        double bmin = kInf, bmax = -kInf;                  // over ALL band entries (tie blocks > 32)
         int mine_pos = 0;
         for (int e0 = 0; e0 < cnt; e0 += 32) {
           const int e = e0 + lane;
@@ -633,6 +645,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
           const unsigned bal = __ballot_sync(0xffffffffu, inb);
           const int slot = n_band + __popc(bal & lt);
           const double ex = inb ? exact_d2(kpos) : 0.0;
+          if (inb) { bmin = fmin(bmin, ex); bmax = fmax(bmax, ex); }
           for (unsigned rem = bal; rem; rem &= rem - 1) {
             const int srcl = __ffs(rem) - 1;
             const int dst = __shfl_sync(0xffffffffu, slot, srcl);
@@ -642,19 +655,29 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
           }
           n_band += __popc(bal);
         }
-        if (n_band > 32) { if (lane == 0) atomicOr(flags, 1); }
         const int need = k_nn - n_low;                     // 1-based rank inside the band
-        int rank = 0;
-        if (n_band > 1)
-          for (int l2 = 0; l2 < 32; ++l2) {
-            const double vv = __shfl_sync(0xffffffffu, mine, l2);
-            rank += (vv < mine) || (vv == mine && l2 < lane);
-          }
-        const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < min(n_band, 32));
-        if (hitl) rk2 = __shfl_sync(0xffffffffu, mine, __ffs(hitl) - 1);
-        else if (lane == 0) atomicOr(flags, 1);
+        bool tie_block = false;                            // > 32 band entries, all exactly equal
+        if (n_band > 32) {
+          bmin = warp_min(bmin); bmax = warp_max(bmax);
+          tie_block = bmin == bmax;
+          if (!tie_block && lane == 0) atomicOr(flags, 1);
+        }
+        if (tie_block) {
+          rk2 = bmin;                                      // every rank inside the block has this value
+        } else {
+          int rank = 0;
+          if (n_band > 1)
+            for (int l2 = 0; l2 < 32; ++l2) {
+              const double vv = __shfl_sync(0xffffffffu, mine, l2);
+              rank += (vv < mine) || (vv == mine && l2 < lane);
+            }
+          const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < min(n_band, 32));
+          if (hitl) rk2 = __shfl_sync(0xffffffffu, mine, __ffs(hitl) - 1);
+          else if (lane == 0) atomicOr(flags, 1);
+        }
         cut = fmin(rk2, r2_max);
-        if (fused) {
+        if (fused && n_band > 32) emitted = 0;             // the registers hold 32 of the band: emit from the list
+        if (fused && n_band <= 32) {
           const bool in = lane < min(n_band, 32) && mine <= cut;
           const unsigned bal = __ballot_sync(0xffffffffu, in);
           const int slot = emitted + __popc(bal & lt);

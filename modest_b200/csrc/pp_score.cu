@@ -18,6 +18,8 @@
 //     accumulated with one red.global.add per (query, traversal) hit into counts laid out
 //     [traversal][sorted query position] (spatial neighbours share sectors).
 //   * entropy pass: per sorted query position, T counts -> H in f64 -> pp[original index].
+#include <algorithm>
+
 #include "grid2d.cuh"
 
 namespace modest {
@@ -457,6 +459,421 @@ __global__ void __launch_bounds__(256) pp_entropy_kernel(
   }
 }
 
+// ==== tiled path (round 2): coarse spatial partition + per-tile shared-memory join ================
+// The history pass above probes a global hash grid from every history point; what bounds it is
+// the number of scattered global accesses per point.  The tiled path makes every
+// scattered access a shared-memory access:
+//   * the (x,y) cell grid is cut into tiles of TW x TW columns.  K1 derives, from the query
+//     index, how many query points every tile holds (and where: TW contiguous segments of the
+//     (y,x,z)-sorted query);
+//   * A0/A1 (pp_hist_tile_kernel) stream the history twice, coalesced: count, then scatter
+//     float4{x,y,z,traversal} records into one contiguous bin per tile that holds query points.
+//     A history point goes to its own tile and to every neighbouring tile whose one-cell halo it
+//     touches (1.56 copies on average for TW = 8), so that a tile's bin holds EVERY history point
+//     that can be within the radius of one of the tile's query points.  The atomics of the own
+//     tile are aggregated per warp (lidar order is azimuth-coherent: a warp's 32 points fall
+//     into a few tiles);
+//   * the join (pp_join_kernel, persistent CTAs pulling work items heaviest first) keeps a tile's
+//     query points and their per-traversal counters in shared memory, streams the tile's bin in
+//     chunks of kChunk records, counting-sorts every chunk by (column, z-cell) inside shared
+//     memory (u16 table over the (TW+2)^2 columns x the z-cells the tile's queries can reach,
+//     rank from the histogram atomic), then every query lane walks the cells around it.  Tiles
+//     with few query points spread each query's candidates over several lanes.  Counts are
+//     complete when the bin is consumed, so the entropy is written from shared memory: no global
+//     count array, no global atomics per hit.
+// Work is done in groups of scans small enough for the bins to stay L2-resident between the
+// scatter and the join.
+constexpr int kJoinThreads = 256;                       // CTA items: one CTA per item, kChunk records per pass
+constexpr int kChunk = 2048;
+constexpr int kWarpThreads = 32;                        // warp items (small tiles): one warp per item
+constexpr int kWarpChunk = 256;
+constexpr int kPtsPerThreadJ = 8;                       // records a thread holds while a chunk is sorted
+constexpr int kTagShift = 8;                            // a record's w = traversal << kTagShift
+constexpr int kJoinMaxT = 32;                           // traversals per scan the tiled path accepts
+constexpr int kHeavyBin = 2 * kChunk;                   // bins at least this long: 64 queries per CTA item
+constexpr int kQCapCta = kJoinThreads, kQCapHeavy = 64, kQCapWarp = kWarpThreads;
+constexpr int kWarpMaxRecords = 2048, kWarpMaxQueries = 64;   // tiles up to this size are warp items
+constexpr int kFullColumnZ = 4;                         // z-extent up to which a column is taken whole
+
+template <int TW>
+struct PPItemT {               // one unit of join work: <= 256 query points of one tile
+  int scan;
+  short tx, ty;
+  int k0, nq;                  // k0 = rank of the item's first query inside the tile's query list
+  long long boff;              // first record of the tile's bin
+  double logT;                 // ln(traversals of the scan)
+  int bcnt, pad;
+  int seg_start[TW];           // the tile's query list = TW segments of the sorted query (per row)
+  int seg_len[TW];
+};
+
+struct PPGroupCtr {            // per group of scans, zeroed before use
+  unsigned long long total;    // bin records reserved so far
+  int n_cta, n_warp;           // CTA items are appended at the front, warp items at the back of the item array
+  int next_cta, next_warp;     // work counters of the two join kernels
+};
+
+template <int TW, int NTHR> struct TileGeo {
+  static constexpr int WW = TW + 2;                                       // tile + halo, in columns
+  static constexpr int kCellsMax = WW * WW * kZCells;
+  static constexpr int kWptMax = (((kCellsMax + 2) / 2 + NTHR - 1) / NTHR) | 1;
+  static constexpr int kTblWords = kWptMax * NTHR;
+};
+
+// K1: query points per tile and their segments in the sorted query
+template <int TW>
+__global__ void __launch_bounds__(256) pp_tile_query_kernel(
+    const int2* __restrict__ cols, const int* __restrict__ zc, const int64_t* __restrict__ q_off,
+    const PPMeta* __restrict__ meta, int G, int NT1, int* __restrict__ tile_nq, int2* __restrict__ tile_seg) {
+  const int s = blockIdx.y;
+  const int NT = NT1 * NT1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= NT) return;
+  const int n = meta[s].n;
+  const int2* __restrict__ c = cols + (size_t)s * pp_col_stride(G);
+  const int* __restrict__ z = zc + zc_offset(q_off, s);
+  const int ty = t / NT1, tx = t - ty * NT1;
+  const int ncol = G * G;
+  auto qstart = [&](int lin) { return lin < ncol ? __ldg(z + __ldg(&c[lin].x)) : n; };
+  int total = 0;
+  int2 seg[TW];
+#pragma unroll
+  for (int r = 0; r < TW; ++r) {
+    const int lin0 = (ty * TW + r) * G + tx * TW;
+    const int a = qstart(lin0), b = qstart(lin0 + TW);
+    seg[r] = make_int2(a, b - a);
+    total += b - a;
+  }
+  tile_nq[(size_t)s * NT + t] = total;
+  if (total > 0) {
+    int2* o = tile_seg + ((size_t)s * NT + t) * TW;
+#pragma unroll
+    for (int r = 0; r < TW; ++r) o[r] = seg[r];
+  }
+}
+
+// A0 / A1: stream the history of the group's traversals; count (SCATTER = false) or write
+// (SCATTER = true) one record per (point, tile that needs it).  A record's w is the traversal
+// index << kTagShift.
+template <int TW, bool SCATTER>
+__global__ void __launch_bounds__(256) pp_hist_tile_kernel(
+    const float* __restrict__ h_xyz, const int64_t* __restrict__ h_off, const int32_t* __restrict__ trav_scan,
+    const int32_t* __restrict__ trav_off, int g0, const PPMeta* __restrict__ meta, const int* __restrict__ tile_nq,
+    int* __restrict__ tile_cnt, const long long* __restrict__ tile_boff, float4* __restrict__ bins, int G, int NT1) {
+  const int g = g0 + blockIdx.y;
+  const int s = trav_scan[g];
+  const float tagw = __int_as_float((g - trav_off[s]) << kTagShift);
+  const int64_t hbeg = h_off[g], hn = h_off[g + 1] - hbeg;
+  const PPMeta m = meta[s];
+  const int NT = NT1 * NT1;
+  const int* __restrict__ nq = tile_nq + (size_t)s * NT;
+  int* __restrict__ cnt = tile_cnt + (size_t)s * NT;
+  const long long* __restrict__ boff = tile_boff + (size_t)s * NT;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int64_t warp0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = warp0; base < hn; base += stride) {            // warp-uniform trip count
+    const int64_t i = base + lane;
+    float x = 0.f, y = 0.f, z = 0.f;
+    int key0 = -1, key1 = -1, key2 = -1, key3 = -1;
+    if (i < hn) {
+      const float* p = h_xyz + 3 * (hbeg + i);
+      x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+      if (x == x && y == y && z == z) {                              // removed (NaN) rows never count
+        const int cx = clampi(cell_coord(x, m.x0, m.inv_cell), 0, G - 1);
+        const int cy = clampi(cell_coord(y, m.y0, m.inv_cell), 0, G - 1);
+        const int tx = cx / TW, ty = cy / TW, lx = cx - tx * TW, ly = cy - ty * TW;
+        const int nx = (lx == 0 && tx > 0) ? tx - 1 : ((lx == TW - 1 && tx < NT1 - 1) ? tx + 1 : -1);
+        const int ny = (ly == 0 && ty > 0) ? ty - 1 : ((ly == TW - 1 && ty < NT1 - 1) ? ty + 1 : -1);
+        key0 = ty * NT1 + tx;
+        if (__ldg(nq + key0) == 0) key0 = -1;                          // nobody to count for over there
+        if (nx >= 0 && __ldg(nq + ty * NT1 + nx) != 0) key1 = ty * NT1 + nx;
+        if (ny >= 0 && __ldg(nq + ny * NT1 + tx) != 0) key2 = ny * NT1 + tx;
+        if (nx >= 0 && ny >= 0 && __ldg(nq + ny * NT1 + nx) != 0) key3 = ny * NT1 + nx;
+      }
+    }
+    // own tile: one atomic per (warp, tile); halo copies (a quarter of the lanes): one each.
+    // All four are issued before any result is used.
+    const unsigned grp = __match_any_sync(0xffffffffu, key0);
+    const int leader = __ffs(grp) - 1;
+    if (SCATTER) {
+      int first = 0, p1 = 0, p2 = 0, p3 = 0;
+      if (key0 >= 0 && lane == leader) first = atomicAdd(cnt + key0, __popc(grp));
+      if (key1 >= 0) p1 = atomicAdd(cnt + key1, 1);
+      if (key2 >= 0) p2 = atomicAdd(cnt + key2, 1);
+      if (key3 >= 0) p3 = atomicAdd(cnt + key3, 1);
+      first = __shfl_sync(0xffffffffu, first, leader);
+      const float4 rec = make_float4(x, y, z, tagw);
+      if (key0 >= 0) bins[boff[key0] + first + __popc(grp & lt)] = rec;
+      if (key1 >= 0) bins[boff[key1] + p1] = rec;
+      if (key2 >= 0) bins[boff[key2] + p2] = rec;
+      if (key3 >= 0) bins[boff[key3] + p3] = rec;
+    } else {
+      if (key0 >= 0 && lane == leader) atomicAdd(cnt + key0, __popc(grp));
+      if (key1 >= 0) atomicAdd(cnt + key1, 1);
+      if (key2 >= 0) atomicAdd(cnt + key2, 1);
+      if (key3 >= 0) atomicAdd(cnt + key3, 1);
+    }
+  }
+}
+
+// K3: bin offsets and work items.  One thread per tile; bins and items may come in any order, so
+// a warp reserves the space of its 32 tiles with one atomic per quantity.  Small tiles become
+// warp items (one warp sorts and joins the whole tile), the others CTA items.
+template <int TW>
+__global__ void __launch_bounds__(256) pp_tile_plan_kernel(
+    int s0, int NT1, const int* __restrict__ tile_nq, const int* __restrict__ tile_hcnt, const int2* __restrict__ tile_seg,
+    const int32_t* __restrict__ trav_off, long long* __restrict__ tile_boff, PPItemT<TW>* __restrict__ items, int item_cap,
+    PPGroupCtr* __restrict__ ctr) {
+  const int s = s0 + blockIdx.y;
+  const int NT = NT1 * NT1;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int q = 0, h = 0;
+  if (t < NT) {
+    q = tile_nq[(size_t)s * NT + t];
+    if (q > 0) h = tile_hcnt[(size_t)s * NT + t];
+  }
+  const bool warp_item = h <= kWarpMaxRecords && q <= kWarpMaxQueries;
+  const int cap = warp_item ? kQCapWarp : (h >= kHeavyBin ? kQCapHeavy : kQCapCta);
+  const int n_it = q > 0 ? (q + cap - 1) / cap : 0;
+  int ih = h, iC = warp_item ? 0 : n_it, iW = warp_item ? n_it : 0;
+  const int sh = ih, sC = iC, sW = iW;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int uh = __shfl_up_sync(0xffffffffu, ih, o), uC = __shfl_up_sync(0xffffffffu, iC, o),
+              uW = __shfl_up_sync(0xffffffffu, iW, o);
+    if (lane >= o) { ih += uh; iC += uC; iW += uW; }
+  }
+  long long bh = 0;
+  int bC = 0, bW = 0;
+  if (lane == 31) {
+    if (ih) bh = (long long)atomicAdd(&ctr->total, (unsigned long long)ih);
+    if (iC) bC = atomicAdd(&ctr->n_cta, iC);
+    if (iW) bW = atomicAdd(&ctr->n_warp, iW);
+  }
+  bh = __shfl_sync(0xffffffffu, bh, 31) + ih - sh;
+  bC = __shfl_sync(0xffffffffu, bC, 31) + iC - sC;
+  bW = __shfl_sync(0xffffffffu, bW, 31) + iW - sW;
+  if (q <= 0) return;
+  tile_boff[(size_t)s * NT + t] = bh;
+  const int2* seg = tile_seg + ((size_t)s * NT + t) * TW;
+  PPItemT<TW> it;
+  it.scan = s; it.ty = (short)(t / NT1); it.tx = (short)(t - (t / NT1) * NT1);
+  it.boff = bh; it.bcnt = h; it.pad = 0;
+  it.logT = log((double)(trav_off[s + 1] - trav_off[s]));
+#pragma unroll
+  for (int r = 0; r < TW; ++r) { const int2 sg = seg[r]; it.seg_start[r] = sg.x; it.seg_len[r] = sg.y; }
+  for (int k0 = 0; k0 < q; k0 += cap) {
+    const int idx = warp_item ? item_cap - 1 - (bW++) : bC++;
+    if (idx < 0 || idx >= item_cap) continue;                        // cannot happen: capacity is an upper bound
+    it.k0 = k0; it.nq = min(cap, q - k0);
+    items[idx] = it;
+  }
+}
+
+// K5: the join.  Persistent blocks of NTHR threads (256: CTA items from the front of the item
+// array, 32: warp items from its back); dynamic shared memory = chunk | cell table | counters.
+template <int TW, int NTHR, int CHUNK>
+__global__ void __launch_bounds__(NTHR, NTHR == 32 ? 16 : 3) pp_join_kernel(
+    const PPItemT<TW>* __restrict__ items, int item_cap, PPGroupCtr* __restrict__ ctr, const float4* __restrict__ sorted,
+    const int64_t* __restrict__ q_off, const PPMeta* __restrict__ meta, const int32_t* __restrict__ trav_off,
+    const int64_t* __restrict__ count_off, const float4* __restrict__ bins, int G, float r2f, float band, double r2,
+    float* __restrict__ pp, int32_t* __restrict__ counts_out) {
+  using Geo = TileGeo<TW, NTHR>;
+  constexpr bool kWarp = NTHR == 32;
+  constexpr int kTermSlots = CHUNK * 2;                // doubles that fit the chunk buffer
+  constexpr int WW = Geo::WW;
+  extern __shared__ __align__(16) unsigned char s_dyn[];             // chunk | cell table | counters
+  float4* s_h = reinterpret_cast<float4*>(s_dyn);
+  unsigned* s_tbl = reinterpret_cast<unsigned*>(s_dyn + sizeof(float4) * CHUNK);
+  int* s_cnt = reinterpret_cast<int*>(s_dyn + sizeof(float4) * CHUNK + sizeof(unsigned) * Geo::kTblWords);   // [traversal][query]
+  __shared__ int s_warp[8];
+  __shared__ int s_work, s_zlo, s_zhi;
+  __shared__ int s_qorig[NTHR];
+  __shared__ PPItemT<TW> s_item;
+  const unsigned short* s_start = reinterpret_cast<const unsigned short*>(s_tbl);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float lo = r2f - band, hi = r2f + band;
+  const int n_items = kWarp ? ctr->n_warp : ctr->n_cta;
+  while (true) {
+    if (tid == 0) { s_work = atomicAdd(kWarp ? &ctr->next_warp : &ctr->next_cta, 1); s_zlo = kZCells; s_zhi = -1; }
+    __syncthreads();
+    const int wk = s_work;
+    if (wk >= n_items) break;
+    const PPItemT<TW>* gi = items + (kWarp ? item_cap - 1 - wk : wk);
+    if (tid < (int)(sizeof(PPItemT<TW>) / 4)) reinterpret_cast<int*>(&s_item)[tid] = reinterpret_cast<const int*>(gi)[tid];
+    __syncthreads();
+    const int s = s_item.scan, nq = s_item.nq;
+    const PPMeta m = meta[s];
+    const int T = trav_off[s + 1] - trav_off[s];
+    const int wx0 = s_item.tx * TW - 1, wy0 = s_item.ty * TW - 1;     // window origin in cells
+    const long long boff = s_item.boff;
+    const int bcnt = s_item.bcnt;
+    // lanes per query: tiles with few query points spread a query's candidates over 2..32 lanes
+    int lsh = 0;
+    while (lsh < 5 && (2 << lsh) * nq <= NTHR) ++lsh;
+    const int lpq = 1 << lsh;
+    const int qi = tid >> lsh, sub = tid & (lpq - 1);
+    const bool has_q = qi < nq;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    int qcol = 0, qz = 0;
+    if (has_q) {
+      int k = s_item.k0 + qi, r = 0;
+      while (r < TW - 1 && k >= s_item.seg_len[r]) { k -= s_item.seg_len[r]; ++r; }
+      q = __ldg(sorted + q_off[s] + s_item.seg_start[r] + k);
+      const int cx = clampi(cell_coord(q.x, m.x0, m.inv_cell), 0, G - 1);
+      const int cy = clampi(cell_coord(q.y, m.y0, m.inv_cell), 0, G - 1);
+      qz = clampi(cell_coord(q.z, m.z0, m.inv_cell), 0, kZCells - 1);
+      qcol = (cy - wy0) * WW + (cx - wx0);                          // an interior column of the window
+      if (sub == 0) {
+        s_qorig[qi] = __float_as_int(q.w);
+        atomicMin(&s_zlo, qz);
+        atomicMax(&s_zhi, qz);
+      }
+    }
+    for (int t = 0; t < T; ++t) s_cnt[t * NTHR + tid] = 0;
+    __syncthreads();
+    // z-cells a record must lie in to matter to one of these queries
+    const int zlo = max(s_zlo - 1, 0), zhi = min(s_zhi + 1, kZCells - 1);
+    const int nz = zhi - zlo + 1;
+    const bool full_col = nz <= kFullColumnZ;                        // short columns are taken whole: 3 ranges per query
+    const int ncell = WW * WW * nz;
+    const int wpt = (((ncell + 2) / 2 + NTHR - 1) / NTHR) | 1;   // table words per thread (odd: no bank conflicts)
+    const int za = max(qz - 1, zlo) - zlo, zb1 = min(qz + 1, zhi) + 1 - zlo;
+    int* cntq = s_cnt + qi;
+
+    for (int c0 = 0; c0 < bcnt; c0 += CHUNK) {
+      const int n = min(CHUNK, bcnt - c0);
+      // ---- counting sort of the chunk by fine cell, in shared memory ----
+      for (int i = tid; i < wpt * NTHR; i += NTHR) s_tbl[i] = 0u;
+      __syncthreads();
+      float4 h[kPtsPerThreadJ];
+      int cr[kPtsPerThreadJ];                                        // cell | rank << 14
+#pragma unroll
+      for (int j = 0; j < kPtsPerThreadJ; ++j) {
+        const int i = tid + j * NTHR;
+        if (i < n) h[j] = __ldg(bins + boff + c0 + i);
+      }
+#pragma unroll
+      for (int j = 0; j < kPtsPerThreadJ; ++j) {
+        const int i = tid + j * NTHR;
+        cr[j] = -1;
+        if (i < n) {
+          const int cz = clampi(cell_coord(h[j].z, m.z0, m.inv_cell), 0, kZCells - 1);
+          if (cz >= zlo && cz <= zhi) {
+            const int cx = clampi(cell_coord(h[j].x, m.x0, m.inv_cell), 0, G - 1);
+            const int cy = clampi(cell_coord(h[j].y, m.y0, m.inv_cell), 0, G - 1);
+            const int wx = clampi(cx - wx0, 0, WW - 1), wy = clampi(cy - wy0, 0, WW - 1);
+            const int cell = (wy * WW + wx) * nz + (cz - zlo);
+            const unsigned old = atomicAdd(&s_tbl[cell >> 1], (cell & 1) ? 0x10000u : 1u);
+            cr[j] = cell | (int)(((cell & 1) ? (old >> 16) : (old & 0xffffu)) << 14);
+          }
+        }
+      }
+      __syncthreads();
+      {   // exclusive scan of the u16 cell counts (two per word), wpt consecutive words per thread
+        int sum = 0;
+        for (int i = 0; i < wpt; ++i) {
+          const unsigned v = s_tbl[tid * wpt + i];
+          sum += (int)(v & 0xffffu) + (int)(v >> 16);
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += u;
+        }
+        int run = incl - sum;
+        if (!kWarp) {
+          if (lane == 31) s_warp[wid] = incl;
+          __syncthreads();
+          for (int k = 0; k < wid; ++k) run += s_warp[k];
+        }
+        for (int i = 0; i < wpt; ++i) {
+          const unsigned v = s_tbl[tid * wpt + i];
+          const unsigned c_lo = v & 0xffffu, c_hi = v >> 16;
+          s_tbl[tid * wpt + i] = (unsigned)run | ((unsigned)(run + c_lo) << 16);
+          run += (int)(c_lo + c_hi);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < kPtsPerThreadJ; ++j)
+        if (cr[j] >= 0) s_h[s_start[cr[j] & 0x3fff] + (cr[j] >> 14)] = h[j];
+      __syncthreads();
+      // ---- every query walks the cells around it; its lanes interleave over the concatenation ----
+      if (has_q) {
+        int skip = sub;
+        auto walk = [&](int kb, int ke) {
+          int c = kb + skip;
+          while (c < ke) {
+            const float4 p = s_h[c];
+            const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
+            const float d2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+            if (d2 <= hi && (d2 < lo || sqdist_f64_seq(q.x, q.y, q.z, p.x, p.y, p.z) <= r2))
+              atomicAdd(cntq + (__float_as_int(p.w) >> kTagShift) * NTHR, 1);
+            c += lpq;
+          }
+          skip = c - ke;
+        };
+        if (full_col) {
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy) {
+            const int b0 = (qcol + dy * WW - 1) * nz;
+            walk(s_start[b0], s_start[b0 + 3 * nz]);
+          }
+        } else {
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              const int b0 = (qcol + dy * WW + dx) * nz;
+              walk(s_start[b0 + za], s_start[b0 + zb1]);
+            }
+        }
+      }
+      __syncthreads();                                               // table and chunk are rewritten next pass
+    }
+    // ---- counts complete: entropy straight from shared memory ----
+    const double logT = s_item.logT;
+    if (nq * T <= kTermSlots) {
+      // one (query, traversal) term per thread and trip: all lanes busy with the f64 log
+      double* s_denom = reinterpret_cast<double*>(s_tbl);
+      double* s_term = reinterpret_cast<double*>(s_h);
+      if (tid < nq) {
+        long long tot = 0;
+        for (int t = 0; t < T; ++t) tot += s_cnt[t * NTHR + tid];
+        s_denom[tid] = __dadd_rn((double)tot, 1e-8);
+      }
+      __syncthreads();
+      for (int p = tid; p < nq * T; p += NTHR) {
+        const int t = p / nq, k = p - t * nq;
+        const int ct = s_cnt[t * NTHR + k];
+        double term = 0.0;                                           // -0.0 * ln(1e-8) is exactly +0.0
+        if (ct != 0) {
+          const double P = __ddiv_rn((double)ct, s_denom[k]);
+          term = __dmul_rn(-P, log(__dadd_rn(P, 1e-8)));
+        }
+        s_term[p] = term;
+      }
+      __syncthreads();
+      if (tid < nq) {
+        double acc = 0.0;
+        for (int t = 0; t < T; ++t) acc = __dadd_rn(acc, s_term[t * nq + tid]);
+        pp[q_off[s] + s_qorig[tid]] = (float)__ddiv_rn(acc, logT);
+      }
+    } else if (tid < nq) {
+      pp[q_off[s] + s_qorig[tid]] = pp_entropy_of(T, logT, [&](int t) { return s_cnt[t * NTHR + tid]; });
+    }
+    if (counts_out && tid < nq)
+      for (int t = 0; t < T; ++t)
+        counts_out[count_off[s] + (size_t)s_qorig[tid] * T + t] = s_cnt[t * NTHR + tid];
+    __syncthreads();                                                 // s_item / s_cnt / s_tbl are rewritten by the next item
+  }
+}
+
 __global__ void pp_trav_scan_kernel(const int32_t* __restrict__ trav_off, int n_scans, int32_t* __restrict__ trav_scan) {
   const int s = blockIdx.x;
   if (s >= n_scans) return;
@@ -529,7 +946,142 @@ static const int kMaxTraversals = 1 << 16;
 
 static int col_tiles(int G) { return (int)(((size_t)G * G + kColTile - 1) / kColTile); }
 
-extern "C" size_t modest_pp_workspace_bytes(int n_scans, int64_t n_query_total, int64_t n_count_total, int grid_dim) {
+// ---- grouping of the tiled path (host) -------------------------------------------------------------
+// Consecutive scans are processed together while their history stays below `group_points`
+// points, so that a group's bins (written by the scatter, read by the join) stay L2-resident.
+// A history point is copied into at most 4 tiles, which bounds a group's bin records.
+static const int64_t kDefaultGroupPoints = 2 * 1000 * 1000;
+static const int kMaxBinCopies = 4;
+
+static int64_t scan_hist_points(const int64_t* h_h_off, const int32_t* h_trav_off, int s) {
+  return h_h_off[h_trav_off[s + 1]] - h_h_off[h_trav_off[s]];
+}
+// end (exclusive) of the group that starts at scan s0
+static int group_end(const int64_t* h_h_off, const int32_t* h_trav_off, int n_scans, int s0, int64_t group_points) {
+  int64_t pts = 0;
+  int s = s0;
+  while (s < n_scans) {
+    const int64_t p = scan_hist_points(h_h_off, h_trav_off, s);
+    if (s > s0 && pts + p > group_points) break;
+    pts += p;
+    ++s;
+  }
+  return s;
+}
+
+static size_t pp_item_capacity(int n_scans, int64_t n_query_total, int NT) {
+  return (size_t)n_scans * NT + (size_t)(n_query_total / kQCapWarp) + (size_t)n_scans + 1;
+}
+
+constexpr int kTWMin = 8, kTWMax = 8;             // tile edge in cells (the kernels are templates on it)
+
+struct PPTiledWs {
+  int* tile_nq;                 // [3][n_scans][NT]: query points, history records, scatter cursor
+  long long* tile_boff;
+  int2* tile_seg;
+  void* items;
+  PPGroupCtr* ctrs;
+  float4* bins;
+};
+struct PPTiledArgs {
+  const float* d_hist_xyz; const int64_t* d_h_off; const int32_t* d_trav_off; const int64_t* d_q_off;
+  const int64_t* d_count_off; float* d_pp; int32_t* d_counts;
+  const int64_t* h_q_off; const int64_t* h_h_off; const int32_t* h_trav_off;
+  int n_scans; int64_t n_query_total; int64_t group_points; int64_t bin_records; int t_max; int G;
+  float r2f, band; double r2;
+  const PPMeta* meta; const int2* cols; const int* zc; const float4* sorted; const int32_t* trav_scan;
+};
+
+template <int TW>
+static int pp_tiled_run(const PPTiledArgs& a, const PPTiledWs& w, cudaStream_t stream, int* launched) {
+  const int G = a.G, NT1 = G / TW, NT = NT1 * NT1, n_scans = a.n_scans;
+  int* tile_nq = w.tile_nq;
+  int* tile_hcnt = tile_nq + (size_t)n_scans * NT;
+  int* tile_fill = tile_hcnt + (size_t)n_scans * NT;
+  PPItemT<TW>* items = static_cast<PPItemT<TW>*>(w.items);
+  const size_t cta_fixed = sizeof(float4) * kChunk + sizeof(unsigned) * TileGeo<TW, kJoinThreads>::kTblWords;
+  const size_t warp_fixed = sizeof(float4) * kWarpChunk + sizeof(unsigned) * TileGeo<TW, kWarpThreads>::kTblWords;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MODEST_CUDA(cudaFuncSetAttribute(pp_join_kernel<TW, kJoinThreads, kChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(cta_fixed + kJoinMaxT * kJoinThreads * sizeof(int))));
+    MODEST_CUDA(cudaFuncSetAttribute(pp_join_kernel<TW, kWarpThreads, kWarpChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(warp_fixed + kJoinMaxT * kWarpThreads * sizeof(int))));
+    attr_set = true;
+  }
+  MODEST_CUDA(cudaMemsetAsync(tile_hcnt, 0, sizeof(int) * (size_t)n_scans * NT * 2, stream));   // + tile_fill
+  MODEST_CUDA(cudaMemsetAsync(w.ctrs, 0, sizeof(PPGroupCtr) * (size_t)n_scans, stream));
+  pp_tile_query_kernel<TW><<<dim3((NT + 255) / 256, n_scans), 256, 0, stream>>>(a.cols, a.zc, a.d_q_off, a.meta, G, NT1, tile_nq,
+                                                                               w.tile_seg);
+  MODEST_LAUNCH_CHECK("pp_tile_query_kernel");
+  ++*launched;
+  const int join_ctas = sm_count() * 3, join_warps = sm_count() * 16;
+  const size_t cta_smem = cta_fixed + (size_t)std::max(a.t_max, 1) * kJoinThreads * sizeof(int);
+  const size_t warp_smem = warp_fixed + (size_t)std::max(a.t_max, 1) * kWarpThreads * sizeof(int);
+  int grp = 0;
+  for (int s0 = 0; s0 < n_scans; ++grp) {
+    const int s1 = group_end(a.h_h_off, a.h_trav_off, n_scans, s0, a.group_points);
+    const int g0 = a.h_trav_off[s0], g1 = a.h_trav_off[s1];
+    const int64_t pts = a.h_h_off[g1] - a.h_h_off[g0];
+    MODEST_REQUIRE(kMaxBinCopies * pts + 16 <= a.bin_records,
+                   "pp_score: bin_records %lld too small for a group of %lld history points (use modest_pp_bin_records)",
+                   (long long)a.bin_records, (long long)pts);
+    int64_t gmax = 0, gq = 0;
+    for (int g = g0; g < g1; ++g) gmax = std::max(gmax, (int64_t)(a.h_h_off[g + 1] - a.h_h_off[g]));
+    for (int s = s0; s < s1; ++s) gq += a.h_q_off[s + 1] - a.h_q_off[s];
+    const int item_cap = (int)pp_item_capacity(s1 - s0, gq, NT);
+    int64_t hb = std::min<int64_t>(std::max<int64_t>((gmax + 255) / 256, 1), 4096);
+    const dim3 hgrid((unsigned)hb, std::max(g1 - g0, 1));
+    const bool any_hist = g1 > g0 && pts > 0;
+    if (any_hist) {
+      pp_hist_tile_kernel<TW, false><<<hgrid, 256, 0, stream>>>(a.d_hist_xyz, a.d_h_off, a.trav_scan, a.d_trav_off, g0, a.meta,
+                                                               tile_nq, tile_hcnt, nullptr, nullptr, G, NT1);
+      MODEST_LAUNCH_CHECK("pp_hist_tile_kernel<count>");
+      ++*launched;
+    }
+    pp_tile_plan_kernel<TW><<<dim3((NT + 255) / 256, s1 - s0), 256, 0, stream>>>(s0, NT1, tile_nq, tile_hcnt, w.tile_seg, a.d_trav_off,
+                                                                                w.tile_boff, items, item_cap, w.ctrs + grp);
+    MODEST_LAUNCH_CHECK("pp_tile_plan_kernel");
+    if (any_hist) {
+      pp_hist_tile_kernel<TW, true><<<hgrid, 256, 0, stream>>>(a.d_hist_xyz, a.d_h_off, a.trav_scan, a.d_trav_off, g0, a.meta,
+                                                              tile_nq, tile_fill, w.tile_boff, w.bins, G, NT1);
+      MODEST_LAUNCH_CHECK("pp_hist_tile_kernel<scatter>");
+      ++*launched;
+    }
+    // scans without any history still get their (zero) scores from the join; the big tiles
+    // (CTA items) start first, the many small ones (warp items) fill in around them
+    pp_join_kernel<TW, kJoinThreads, kChunk><<<join_ctas, kJoinThreads, cta_smem, stream>>>(
+        items, item_cap, w.ctrs + grp, a.sorted, a.d_q_off, a.meta, a.d_trav_off, a.d_count_off, w.bins, G, a.r2f, a.band, a.r2,
+        a.d_pp, a.d_counts);
+    MODEST_LAUNCH_CHECK("pp_join_kernel<cta>");
+    pp_join_kernel<TW, kWarpThreads, kWarpChunk><<<join_warps, kWarpThreads, warp_smem, stream>>>(
+        items, item_cap, w.ctrs + grp, a.sorted, a.d_q_off, a.meta, a.d_trav_off, a.d_count_off, w.bins, G, a.r2f, a.band, a.r2,
+        a.d_pp, a.d_counts);
+    MODEST_LAUNCH_CHECK("pp_join_kernel<warp>");
+    *launched += 3;
+    s0 = s1;
+  }
+  return MODEST_OK;
+}
+
+extern "C" int64_t modest_pp_bin_records(const int64_t* h_h_off, const int32_t* h_trav_off, int n_scans,
+                                         int64_t group_points) {
+  if (!h_h_off || !h_trav_off || n_scans <= 0) return 0;
+  if (group_points <= 0) group_points = kDefaultGroupPoints;
+  int64_t worst = 0;
+  for (int s0 = 0; s0 < n_scans;) {
+    const int s1 = group_end(h_h_off, h_trav_off, n_scans, s0, group_points);
+    const int64_t pts = h_h_off[h_trav_off[s1]] - h_h_off[h_trav_off[s0]];
+    if (pts > worst) worst = pts;
+    s0 = s1;
+  }
+  return kMaxBinCopies * worst + 16;
+}
+
+
+
+extern "C" size_t modest_pp_workspace_bytes(int n_scans, int64_t n_query_total, int64_t n_count_total, int grid_dim,
+                                            int64_t bin_records) {
   if (grid_dim <= 0) grid_dim = 512;
   size_t b = 0;
   auto add = [&](size_t bytes) { b = align_up(b, 256) + bytes; };
@@ -538,8 +1090,18 @@ extern "C" size_t modest_pp_workspace_bytes(int n_scans, int64_t n_query_total, 
   add(sizeof(int) * ((size_t)n_query_total + 8 * (size_t)n_scans + 8));      // compact cell starts
   add(sizeof(int) * (size_t)n_scans * col_tiles(grid_dim));                  // tile sums
   add(sizeof(float4) * (size_t)n_query_total);                               // sorted query
-  add(sizeof(int) * (size_t)n_count_total);                                  // counts [t][pos]
   add(sizeof(int32_t) * (size_t)kMaxTraversals);                             // traversal -> scan
+  // legacy path: counts [t][pos]; tiled path: the bins -- never both in one call
+  const size_t legacy = sizeof(int) * (size_t)n_count_total, tiled = sizeof(float4) * (size_t)(bin_records > 0 ? bin_records : 0);
+  add(legacy > tiled ? legacy : tiled);
+  if (bin_records > 0 && grid_dim % kTWMax == 0) {
+    const int NT = (grid_dim / kTWMin) * (grid_dim / kTWMin);
+    add(sizeof(int) * (size_t)n_scans * NT * 3);                             // tile_nq, tile_hcnt, tile_fill
+    add(sizeof(long long) * (size_t)n_scans * NT);                           // tile_boff
+    add(sizeof(int2) * (size_t)n_scans * NT * kTWMin);                       // tile_seg
+    add(sizeof(PPItemT<kTWMax>) * pp_item_capacity(n_scans, n_query_total, NT));
+    add(sizeof(PPGroupCtr) * (size_t)n_scans);
+  }
   return b + 256;
 }
 
@@ -549,7 +1111,9 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
                                      int64_t n_query_total, int64_t n_count_total,
                                      int64_t max_query_points, int64_t max_trav_points, double radius,
                                      int grid_dim, int32_t* d_counts, const int64_t* d_count_off,
-                                     float* d_pp, void* d_ws, size_t ws_bytes, void* stream_) {
+                                     float* d_pp, const int64_t* h_q_off, const int64_t* h_h_off,
+                                     const int32_t* h_trav_off, int64_t group_points, int64_t bin_records,
+                                     void* d_ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (grid_dim <= 0) grid_dim = 512;
   MODEST_REQUIRE(n_scans >= 0 && n_trav_total >= 0, "pp_score: negative sizes");
@@ -561,9 +1125,21 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
   MODEST_REQUIRE(radius > 0.0 && radius < 1e3, "pp_score: radius %g out of range", radius);
   MODEST_REQUIRE(grid_dim >= 8 && grid_dim <= 4096 && grid_dim % 4 == 0,
                  "pp_score: grid_dim %d must be a multiple of 4 in [8,4096]", grid_dim);
-  MODEST_REQUIRE(ws_bytes >= modest_pp_workspace_bytes(n_scans, n_query_total, n_count_total, grid_dim),
+  MODEST_REQUIRE(ws_bytes >= modest_pp_workspace_bytes(n_scans, n_query_total, n_count_total, grid_dim, bin_records),
                  "pp_score: workspace too small (%zu bytes given)", ws_bytes);
   MODEST_REQUIRE(max_query_points < (1ll << 30), "pp_score: a scan has >= 2^30 points");
+
+  // which history pass: the tiled one needs the host copies of the offset tables (to cut the
+  // batch into groups) and at most kJoinMaxT traversals per scan; everything else takes the
+  // global-hash pass (group_points < 0 forces it)
+  bool tiled = h_q_off && h_h_off && h_trav_off && group_points >= 0 && bin_records > 0 && grid_dim % kTWMax == 0 &&
+               n_trav_total > 0 && max_trav_points > 0;
+  int t_max = 0;
+  if (tiled) {
+    for (int s = 0; s < n_scans; ++s) t_max = std::max(t_max, (int)(h_trav_off[s + 1] - h_trav_off[s]));
+    tiled = t_max <= kJoinMaxT;
+  }
+  if (tiled && group_points == 0) group_points = kDefaultGroupPoints;
 
   const int G = grid_dim;
   const size_t ncol = (size_t)G * G;
@@ -575,8 +1151,21 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
   int* zc = ar.take<int>(zc_len);
   int* tile_sums = ar.take<int>((size_t)n_scans * tiles);
   float4* sorted = ar.take<float4>(n_query_total);
-  int* counts = ar.take<int>(n_count_total);
   int32_t* trav_scan = ar.take<int32_t>(kMaxTraversals);
+  const size_t legacy_b = sizeof(int) * (size_t)n_count_total, tiled_b = sizeof(float4) * (size_t)(bin_records > 0 ? bin_records : 0);
+  char* big = ar.take<char>(legacy_b > tiled_b ? legacy_b : tiled_b);
+  int* counts = reinterpret_cast<int*>(big);
+  float4* bins = reinterpret_cast<float4*>(big);
+  PPTiledWs tw = {};
+  if (tiled) {
+    const int NTs = (G / kTWMin) * (G / kTWMin);                              // sized for the finer tiling
+    tw.tile_nq = ar.take<int>((size_t)n_scans * NTs * 3);
+    tw.tile_boff = ar.take<long long>((size_t)n_scans * NTs);
+    tw.tile_seg = ar.take<int2>((size_t)n_scans * NTs * kTWMin);
+    tw.items = ar.take<PPItemT<kTWMax>>(pp_item_capacity(n_scans, n_query_total, NTs));
+    tw.ctrs = ar.take<PPGroupCtr>(n_scans);
+    tw.bins = bins;
+  }
   MODEST_REQUIRE(ar.ok(), "workspace too small for the requested sizes");
 
   const float cell = (float)radius * kCellSlack;
@@ -586,7 +1175,7 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
 
   MODEST_CUDA(cudaMemsetAsync(cols, 0, sizeof(int2) * (size_t)n_scans * ncol, stream));
   MODEST_CUDA(cudaMemsetAsync(zc, 0, sizeof(int) * zc_len, stream));
-  MODEST_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)n_count_total, stream));
+  if (!tiled) MODEST_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)n_count_total, stream));
 
   int qblocks = (int)((max_query_points + 255) / 256);
   if (qblocks < 1) qblocks = 1;
@@ -611,11 +1200,24 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
   pp_scatter_kernel<<<qgrid, 256, 0, stream>>>(d_query_xyz, d_q_off, meta, cols, zc, sorted, G);
   MODEST_LAUNCH_CHECK("pp_scatter_kernel");
   int n_launched = 9;
+  const int slot = g_prof_slots ? (int)(g_prof_calls % g_prof_slots) : -1;
+
+  if (tiled) {
+    if (slot >= 0) cudaEventRecord(g_prof_ev[2 * slot], stream);
+    PPTiledArgs ta = {d_hist_xyz, d_h_off, d_trav_off, d_q_off, d_count_off, d_pp, d_counts, h_q_off, h_h_off, h_trav_off,
+                      n_scans, n_query_total, group_points, bin_records, t_max, G, r2f, band, r2, meta, cols, zc, sorted, trav_scan};
+    int launched = 0;
+    const int rc = pp_tiled_run<kTWMin>(ta, tw, stream, &launched);
+    if (rc != MODEST_OK) return rc;
+    if (slot >= 0) { cudaEventRecord(g_prof_ev[2 * slot + 1], stream); ++g_prof_calls; }
+    note_launch(n_launched + launched);
+    return MODEST_OK;
+  }
+
   if (n_trav_total > 0 && max_trav_points > 0) {
     int64_t hb = (max_trav_points + 255) / 256;
     if (hb > 65535) hb = 65535;
     const dim3 hgrid((unsigned)hb, n_trav_total);   // 8 warps x 32 points per CTA per trip
-    const int slot = g_prof_slots ? (int)(g_prof_calls % g_prof_slots) : -1;
     if (slot >= 0) cudaEventRecord(g_prof_ev[2 * slot], stream);
     pp_count_kernel<<<hgrid, 256, 0, stream>>>(d_hist_xyz, d_h_off, trav_scan, d_trav_off, d_q_off, d_count_off, meta,
                                                cols, zc, sorted, counts, G, r2f, band, r2);

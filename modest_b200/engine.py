@@ -164,7 +164,7 @@ class SeedLabelEngine:
             slot.pp_batch = pp_mod.PPBatch(
                 q, small_d[:a], h, small_d[a:b], trav_d, small_d[b:], n_scans=len(hb.q_sizes), n_trav_total=int(trav_off[-1]),
                 n_query_total=int(q_off[-1]), n_count_total=int(count_off[-1]), max_query_points=tb["max_q"],
-                max_trav_points=tb["max_h"], h_q_off=q_off, h_trav_off=trav_off, h_count_off=count_off)
+                max_trav_points=tb["max_h"], h_q_off=q_off, h_trav_off=trav_off, h_count_off=count_off, h_h_off=h_off)
             pp = slot.buf("pp", (int(q_off[-1]),), torch.float32)
             slot.scan_batch = pl.ScanBatch(ptc=p, off=small_d[:a], pp=pp, calib=calib_d,
                                            P2=tb["P2"], h_off=q_off,

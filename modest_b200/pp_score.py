@@ -29,9 +29,10 @@ class PPBatch:
     n_count_total: int
     max_query_points: int
     max_trav_points: int
-    h_q_off: np.ndarray         # host copies
+    h_q_off: np.ndarray         # host copies (the tiled history pass cuts the batch into groups with them)
     h_trav_off: np.ndarray
     h_count_off: np.ndarray
+    h_h_off: np.ndarray = None
 
     @property
     def algorithmic_bytes(self) -> int:
@@ -62,19 +63,38 @@ def pack_batch(queries, histories, device="cuda") -> PPBatch:
                    n_scans=len(queries), n_trav_total=int(trav_off[-1]), n_query_total=int(q_off[-1]),
                    n_count_total=int(count_off[-1]), max_query_points=max(q_sizes, default=0),
                    max_trav_points=max(h_sizes, default=0), h_q_off=q_off, h_trav_off=trav_off,
-                   h_count_off=count_off)
+                   h_count_off=count_off, h_h_off=h_off)
 
 
 class PPScorer:
-    """Reusable workspace + launch wrapper."""
+    """Reusable workspace + launch wrapper.
 
-    def __init__(self, radius: float = 0.3, grid_dim: int = 512):
+    history_pass="hash" (default): the global-hash pass -- every history point probes the query's
+    hash grid; any number of traversals per scan.
+    history_pass="tiled": coarse spatial partition + per-tile shared-memory join, the batch cut into
+    groups of about `group_points` history points (0 = library default).  Same bits; measured
+    slower than the hash pass on the synthetic Lyft shape, kept selectable."""
+
+    def __init__(self, radius: float = 0.3, grid_dim: int = 512, group_points: int = 0, history_pass: str = "hash"):
         self.radius = float(radius)
         self.grid_dim = int(grid_dim)
+        self.group_points = int(group_points)
+        if history_pass not in ("tiled", "hash"):
+            raise ValueError(history_pass)
+        self.history_pass = history_pass
         self._ws = None
 
-    def _workspace(self, b: PPBatch):
-        need = _lib.lib().modest_pp_workspace_bytes(b.n_scans, b.n_query_total, b.n_count_total, self.grid_dim)
+    def _host_tables(self, b: PPBatch):
+        if self.history_pass != "tiled" or b.h_h_off is None:
+            return None, None, None, 0
+        q = np.ascontiguousarray(b.h_q_off, dtype=np.int64)
+        h = np.ascontiguousarray(b.h_h_off, dtype=np.int64)
+        t = np.ascontiguousarray(b.h_trav_off, dtype=np.int32)
+        rec = _lib.lib().modest_pp_bin_records(h.ctypes.data, t.ctypes.data, b.n_scans, self.group_points)
+        return q, h, t, int(rec)
+
+    def _workspace(self, b: PPBatch, bin_records: int):
+        need = _lib.lib().modest_pp_workspace_bytes(b.n_scans, b.n_query_total, b.n_count_total, self.grid_dim, bin_records)
         if self._ws is None or self._ws.numel() < need or self._ws.device != b.query_xyz.device:
             self._ws = torch.empty(int(need), dtype=torch.uint8, device=b.query_xyz.device)
         return self._ws
@@ -83,23 +103,27 @@ class PPScorer:
                  stream=None) -> torch.Tensor:
         if out is None:
             out = torch.empty(b.n_query_total, dtype=torch.float32, device=b.query_xyz.device)
-        ws = self._workspace(b)
+        hq, hh, ht, rec = self._host_tables(b)
+        ws = self._workspace(b, rec)
+        hp = lambda a: None if a is None else a.ctypes.data
         rc = _lib.lib().modest_pp_score_batch(
             _lib.ptr(b.query_xyz), _lib.ptr(b.q_off), _lib.ptr(b.hist_xyz), _lib.ptr(b.h_off),
             _lib.ptr(b.trav_off), b.n_scans, b.n_trav_total, b.n_query_total, b.n_count_total,
             b.max_query_points, b.max_trav_points, self.radius, self.grid_dim,
-            _lib.ptr(counts), _lib.ptr(b.count_off), _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+            _lib.ptr(counts), _lib.ptr(b.count_off), _lib.ptr(out), hp(hq), hp(hh), hp(ht),
+            self.group_points if self.history_pass == "tiled" else -1, rec, _lib.ptr(ws), ws.numel(),
             _lib.stream_ptr(stream))
         _lib.check(rc, "modest_pp_score_batch")
         return out
 
 
-def count_neighbors_and_score(query_xyz, history, radius=0.3, grid_dim=512, return_counts=False):
+def count_neighbors_and_score(query_xyz, history, radius=0.3, grid_dim=512, return_counts=False,
+                              history_pass="hash", group_points=0):
     """One scan: query (N,>=3), history = list of (M_t,3).  Returns pp (N,) f32 numpy
     [and counts (N,T) int64 like the reference's count_neighbors]."""
     b = pack_batch([query_xyz], [history])
     counts = torch.zeros(b.n_count_total, dtype=torch.int32, device="cuda") if return_counts else None
-    pp = PPScorer(radius, grid_dim)(b, counts=counts)
+    pp = PPScorer(radius, grid_dim, group_points=group_points, history_pass=history_pass)(b, counts=counts)
     torch.cuda.synchronize()
     if return_counts:
         return pp.cpu().numpy(), counts.cpu().numpy().reshape(b.n_query_total, len(history)).astype(np.int64)

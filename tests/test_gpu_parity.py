@@ -21,13 +21,35 @@ def _batch(case, pp):
     return pl.make_batch([case.query], [pp], [case.calib], scan_ids=[case.scan_id])
 
 
+@pytest.mark.parametrize("history_pass", ["hash", "tiled"])
 @pytest.mark.parametrize("name", CASES)
-def test_pp_counts_and_score(golden_case, name):
+def test_pp_counts_and_score(golden_case, name, history_pass):
     case, shape, g = golden_case(name)
-    pp, counts = pp_score.count_neighbors_and_score(case.query_fixed, case.history, return_counts=True)
+    pp, counts = pp_score.count_neighbors_and_score(case.query_fixed, case.history, return_counts=True,
+                                                    history_pass=history_pass)
     assert np.array_equal(counts, g["counts"].astype(np.int64))           # bit-exact integer work
     assert np.abs(pp - g["pp"]).max() <= 1e-4                             # north_star tolerance
     assert (pp != g["pp"]).mean() < 1e-3                                  # in practice equal to the last bit
+
+
+@pytest.mark.parametrize("group_points", [0, 1, 150000])
+def test_pp_tiled_pass_equals_global_hash_pass(golden_case, group_points):
+    """The two history passes (tiled shared-memory join, global hash) give the same counts and
+    the same score bits on a ragged batch, whatever the grouping (1 = every scan its own group)."""
+    from modest_b200 import synth
+    cases = [golden_case("small")[0], golden_case("nusc_small")[0],
+             synth.make_scan_case(31, synth.LYFT, n_traversals=5, n_points=20000),
+             synth.make_scan_case(32, synth.LYFT, n_traversals=2, n_points=3000)]
+    b = pp_score.pack_batch([c.query_fixed for c in cases], [c.history for c in cases])
+    out = {}
+    for mode in ("tiled", "hash"):
+        counts = torch.zeros(b.n_count_total, dtype=torch.int32, device="cuda")
+        pp = pp_score.PPScorer(group_points=group_points, history_pass=mode)(b, counts=counts)
+        torch.cuda.synchronize()
+        out[mode] = (pp.cpu().numpy(), counts.cpu().numpy())
+    assert np.array_equal(out["tiled"][1], out["hash"][1])
+    assert np.array_equal(out["tiled"][0].view(np.uint32), out["hash"][0].view(np.uint32))
+    assert out["tiled"][1].sum() > 0
 
 
 @pytest.mark.parametrize("name", CASES)
