@@ -61,6 +61,18 @@ int modest_transform_frames_batch(const float* d_in, int point_stride,
                                   int64_t max_frame_points, int remove_center,
                                   const float* h_center_box, float* d_out, void* stream);
 
+/* Stage B for the streaming engine (pre_compute_pp_score.py:125-167): raw frames
+ * stay in a device cache (one allocation per velodyne/*.bin) and are addressed by pointer.
+ * d_jobs is an array of n_jobs 96-byte records, built on the host and copied to the device:
+ *     struct { const float* src; int64_t dst_row; int32_t n; int32_t flags; float T[16]; int64_t pad; }
+ * Job j reads n rows of src_stride floats at src and writes rows dst_row .. dst_row+n-1 of d_out
+ * (out_stride floats per row): [x,y,z,1] @ T^T rounded like transform_frames_batch; flags & 1
+ * applies remove_center (NaN rows) with h_center_box; flags & 2 copies the rows unchanged
+ * (columns beyond src_stride are zero) -- used to assemble a batch's raw (N,4) scans. */
+int modest_transform_gather_batch(const void* d_jobs, int n_jobs, int src_stride, int out_stride,
+                                  int64_t max_frame_points, const float* h_center_box, float* d_out,
+                                  void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Stage C+D: persistence-point (PP) score.
  * Replaces count_neighbors() + compute_ephe_score() (pre_compute_pp_score.py:54-75) and the

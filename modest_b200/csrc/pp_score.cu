@@ -909,6 +909,44 @@ __global__ void __launch_bounds__(256) transform_frames_kernel(
 }
 
 
+// Stage B for the streaming engine: the raw frames stay where they are (a device
+// cache of velodyne/*.bin contents, one allocation per frame) and are addressed by pointer; every
+// job (source frame, 4x4, destination row) writes xyz rows of `out_stride` floats -- 3 for the PP
+// inputs (query / history in the fixed frame), 4 to assemble a batch's raw scans (identity, the
+// intensity column copied).  Frame f of the launch is blockIdx.y.
+struct FrameJob {            // 96 bytes, built on the host
+  const float* src;          // (n, src_stride) f32 rows [x,y,z,...]
+  long long dst_row;         // first output row
+  int n, flags;              // flags: 1 = remove_center, 2 = copy rows unchanged (no transform)
+  float T[16];               // row-major 4x4 (float32, as get_relative_pose returns it)
+  long long pad;
+};
+
+__global__ void __launch_bounds__(256) transform_gather_kernel(
+    const FrameJob* __restrict__ jobs, int src_stride, int out_stride, float cx0, float cx1, float cy0, float cy1,
+    float* __restrict__ out) {
+  const FrameJob jb = jobs[blockIdx.y];
+  const float nanv = __int_as_float(0x7fc00000);
+  const bool copy = jb.flags & 2, rc = jb.flags & 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.n; i += gridDim.x * blockDim.x) {
+    const float* p = jb.src + (size_t)src_stride * i;
+    float* o = out + (size_t)out_stride * (jb.dst_row + i);
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    if (copy) {
+      o[0] = x; o[1] = y; o[2] = z;
+      for (int k = 3; k < out_stride; ++k) o[k] = k < src_stride ? __ldg(p + k) : 0.f;
+      continue;
+    }
+    if (rc && x < cx1 && x >= cx0 && y < cy1 && y >= cy0) {
+      o[0] = nanv; o[1] = nanv; o[2] = nanv;
+      continue;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)     // same rounding as transform_frames_kernel (sgemm's k-ordered FMAs)
+      o[j] = fmaf(1.0f, jb.T[4 * j + 3], fmaf(z, jb.T[4 * j + 2], fmaf(y, jb.T[4 * j + 1], __fmul_rn(x, jb.T[4 * j]))));
+  }
+}
+
 }  // namespace modest
 
 using namespace modest;
@@ -1249,5 +1287,29 @@ extern "C" int modest_transform_frames_batch(const float* d_in, int point_stride
       c ? c[3] : 0.f, d_out);
   MODEST_LAUNCH_CHECK("transform_frames_kernel");
   note_launch(1);
+  return MODEST_OK;
+}
+
+extern "C" int modest_transform_gather_batch(const void* d_jobs, int n_jobs, int src_stride, int out_stride,
+                                             int64_t max_frame_points, const float* h_center_box, float* d_out,
+                                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_jobs <= 0 || max_frame_points <= 0) return MODEST_OK;
+  static_assert(sizeof(FrameJob) == 96, "FrameJob is part of the ABI (96 bytes)");
+  MODEST_REQUIRE(d_jobs && d_out, "transform_gather: null pointer argument");
+  MODEST_REQUIRE(src_stride >= 3 && out_stride >= 3 && out_stride <= 8, "transform_gather: strides %d / %d", src_stride, out_stride);
+  int done = 0;
+  const float* c = h_center_box;
+  int64_t blocks = (max_frame_points + 255) / 256;
+  if (blocks > 64) blocks = 64;                      // a frame is ~60k points: 64 CTAs x 4 trips; the grid is wide in y
+  while (done < n_jobs) {                            // gridDim.y <= 65535
+    const int n = std::min(n_jobs - done, 65535);
+    transform_gather_kernel<<<dim3((unsigned)blocks, n), 256, 0, stream>>>(
+        static_cast<const FrameJob*>(d_jobs) + done, src_stride, out_stride, c ? c[0] : 0.f, c ? c[1] : 0.f, c ? c[2] : 0.f,
+        c ? c[3] : 0.f, d_out);
+    MODEST_LAUNCH_CHECK("transform_gather_kernel");
+    note_launch(1);
+    done += n;
+  }
   return MODEST_OK;
 }

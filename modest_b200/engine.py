@@ -22,6 +22,8 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
+from . import _lib
+from . import frames as fr
 from . import pipeline as pl
 from . import pp_score as pp_mod
 
@@ -95,6 +97,8 @@ class _Slot:
         self.scan_batch = None
         self.result = None
         self.host = None
+        self.gathers = []          # stage-B launches of a JobBatch: (d_jobs, n, out_stride, max_points, remove_center, out)
+        self.frame_refs = []       # keeps the cached frames of the batch alive until the slot is reused
 
     def pinned(self, name, shape, dtype):
         t = self.bufs.get(name)
@@ -113,7 +117,15 @@ class _Slot:
 
 
 class SeedLabelEngine:
-    def __init__(self, cfg=None, radius=0.3, grid_dim=512, max_clusters=2048, max_boxes=128, seed=0, depth=2):
+    """process() takes HostBatches (query / history already in the fixed frame, everything crosses
+    PCIe for every scan) or frames.JobBatches (frame ids + poses; raw frames cross PCIe once and
+    stay in `frame_cache`, stage B runs on the GPU -- SURVEY.md 8(f-2)).  `frame_source(fid)` must
+    return a pinned (N,4) float32 host tensor."""
+
+    def __init__(self, cfg=None, radius=0.3, grid_dim=512, max_clusters=2048, max_boxes=128, seed=0, depth=2,
+                 frame_source=None, frame_cache_bytes=48 << 30):
+        self.frame_cache = fr.DeviceFrameCache(frame_source, frame_cache_bytes) if frame_source is not None else None
+        self.h2d_bytes_tables = 0
         self.copy_stream = torch.cuda.Stream()
         # `depth` batches may be computing while the host reads back an older one: the launcher
         # thread runs up to `depth` batches ahead of the consumer, so two lanes of kernels are
@@ -170,12 +182,92 @@ class SeedLabelEngine:
                                            P2=tb["P2"], h_off=q_off,
                                            scan_ids=hb.scan_ids, scan_keys=keys_d)
             slot.host = hb
+            slot.gathers, slot.frame_refs = [], []
+            slot.ready.record(self.copy_stream)
+
+    def _upload_jobs(self, slot: _Slot, jb: "fr.JobBatch"):
+        """JobBatch: upload the frames the cache does not hold yet and the job tables of stage B."""
+        if self.frame_cache is None:
+            raise ValueError("JobBatch given but the engine has no frame_source")
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot.done)                # buffers free again?
+            cache = self.frame_cache
+            q_t = [cache.get(int(f)) for f in jb.query_fid]
+            h_t = [cache.get(int(f)) for f in jb.hist_fid]
+            slot.frame_refs = q_t + h_t
+            S, H = len(q_t), len(h_t)
+            qn = np.array([t.shape[0] for t in q_t], dtype=np.int64)
+            hn = np.array([t.shape[0] for t in h_t], dtype=np.int64)
+            trav_counts = np.array([len(f) for f in jb.frames_per_trav], dtype=np.int64)
+            fpt = np.array([k for f in jb.frames_per_trav for k in f], dtype=np.int64)
+            h_rows = np.concatenate([[0], np.cumsum(hn)]).astype(np.int64)          # first row of every history frame
+            first = np.concatenate([[0], np.cumsum(fpt)]).astype(np.int64)           # first frame of every traversal
+            q_off = np.concatenate([[0], np.cumsum(qn)]).astype(np.int64)
+            h_off = h_rows[first]                                                      # per traversal
+            trav_off = np.concatenate([[0], np.cumsum(trav_counts)]).astype(np.int32)
+            count_off = np.concatenate([[0], np.cumsum(qn * trav_counts)]).astype(np.int64)
+            crow = np.stack([pl.calib_row(c) for c in jb.calibs])
+            P2 = np.stack([pl.calib_P2(c) for c in jb.calibs])
+            # job records: history -> hist buffer, query -> query buffer (both xyz in the fixed frame), raw scans -> ptc
+            jobs = np.zeros(H + 2 * S, dtype=fr.FRAME_JOB)
+            jobs["src"][:H] = [t.data_ptr() for t in h_t]
+            jobs["dst_row"][:H] = h_rows[:-1]
+            jobs["n"][:H] = hn
+            jobs["flags"][:H] = 1 if jb.remove_center else 0
+            jobs["T"][:H] = jb.hist_T.reshape(H, 16)
+            jobs["src"][H:H + S] = jobs["src"][H + S:] = [t.data_ptr() for t in q_t]
+            jobs["dst_row"][H:H + S] = jobs["dst_row"][H + S:] = q_off[:-1]
+            jobs["n"][H:H + S] = jobs["n"][H + S:] = qn
+            jobs["T"][H:H + S] = jb.query_T.reshape(S, 16)
+            jobs["flags"][H + S:] = 2
+            small = np.concatenate([q_off, h_off, count_off]).astype(np.int64)
+            small_h = slot.pinned("off_h", small.shape, torch.int64)
+            trav_h = slot.pinned("trav_h", trav_off.shape, torch.int32)
+            calib_h = slot.pinned("calib_h", crow.shape, torch.float64)
+            keys_h = slot.pinned("keys_h", (S,), torch.int64)
+            jobs_h = slot.pinned("jobs_h", (jobs.nbytes,), torch.uint8)
+            small_h.copy_(torch.from_numpy(small))
+            trav_h.copy_(torch.from_numpy(trav_off))
+            calib_h.copy_(torch.from_numpy(crow))
+            keys_h.copy_(torch.tensor([pl.scan_key(i) for i in jb.scan_ids], dtype=torch.int64))
+            jobs_h.copy_(torch.from_numpy(jobs.view(np.uint8)))
+            small_d = slot.buf("off", small.shape, torch.int64)
+            trav_d = slot.buf("trav", trav_off.shape, torch.int32)
+            calib_d = slot.buf("calib", crow.shape, torch.float64)
+            keys_d = slot.buf("keys", (S,), torch.int64)
+            jobs_d = slot.buf("jobs", (jobs.nbytes,), torch.uint8)
+            for d, h in ((small_d, small_h), (trav_d, trav_h), (calib_d, calib_h), (keys_d, keys_h), (jobs_d, jobs_h)):
+                d.copy_(h, non_blocking=True)
+            self.h2d_bytes_tables += small.nbytes + trav_off.nbytes + crow.nbytes + 8 * S + jobs.nbytes
+            NQ, NH = int(q_off[-1]), int(h_rows[-1])
+            q = slot.buf("q", (NQ, 3), torch.float32)
+            h = slot.buf("h", (NH, 3), torch.float32)
+            p = slot.buf("p", (NQ, 4), torch.float32)
+            jp = jobs_d.data_ptr()
+            slot.gathers = [(jp, H, 3, int(hn.max()) if H else 0, jb.remove_center, h),
+                            (jp + 96 * H, S, 3, int(qn.max()), False, q),
+                            (jp + 96 * (H + S), S, 4, int(qn.max()), False, p)]
+            a, b = len(q_off), len(q_off) + len(h_off)
+            sizes = np.diff(h_off, append=h_rows[-1])
+            slot.pp_batch = pp_mod.PPBatch(
+                q, small_d[:a], h, small_d[a:b], trav_d, small_d[b:], n_scans=S, n_trav_total=int(trav_off[-1]),
+                n_query_total=NQ, n_count_total=int(count_off[-1]), max_query_points=int(qn.max()),
+                max_trav_points=int(sizes.max()) if len(sizes) else 0, h_q_off=q_off, h_trav_off=trav_off,
+                h_count_off=count_off, h_h_off=np.concatenate([h_off, [h_rows[-1]]]).astype(np.int64))
+            pp = slot.buf("pp", (NQ,), torch.float32)
+            slot.scan_batch = pl.ScanBatch(ptc=p, off=small_d[:a], pp=pp, calib=calib_d, P2=P2, h_off=q_off,
+                                           scan_ids=jb.scan_ids, scan_keys=keys_d)
+            slot.host = jb
             slot.ready.record(self.copy_stream)
 
     # ---- stage 2: kernels on the compute stream ---------------------------------------------------
     def _compute(self, slot: _Slot, step: int):
         with torch.cuda.stream(slot.stream):
             slot.stream.wait_event(slot.ready)
+            for (jobs_ptr, n, out_stride, max_n, rc, out) in slot.gathers:      # stage B on the cached raw frames
+                _lib.check(_lib.lib().modest_transform_gather_batch(
+                    jobs_ptr, n, 4, out_stride, max_n, fr.CENTER_BOX.ctypes.data if rc else None, _lib.ptr(out),
+                    _lib.stream_ptr(slot.stream)), "modest_transform_gather_batch")
             slot.scorer(slot.pp_batch, out=slot.scan_batch.pp, stream=slot.stream)
             # one seed for the whole run: the draws of a scan are keyed by its id, not by the
             # step or the batch slot, so batching and sharding do not change its labels
@@ -233,7 +325,7 @@ class SeedLabelEngine:
                     if stop.is_set():
                         return
                     t0 = time.perf_counter()
-                    self._upload(slot, hb)
+                    (self._upload_jobs if isinstance(hb, fr.JobBatch) else self._upload)(slot, hb)
                     t1 = time.perf_counter()
                     self._compute(slot, step)
                     self.host_s["upload"] += t1 - t0

@@ -73,12 +73,12 @@ class World:
         return self.tilt[0] * x + self.tilt[1] * y
 
 
-def make_world(seed: int, n_walls: int = 60, n_poles: int = 40) -> World:
+def make_world(seed: int, n_walls: int = 60, n_poles: int = 40, x_range=(-75.0, 95.0)) -> World:
     rng = np.random.default_rng(seed)
     tilt = np.tan(np.deg2rad(rng.uniform(-0.8, 0.8, size=2)))
     walls = np.zeros((n_walls, 6))
     for i in range(n_walls):
-        cx = rng.uniform(-75, 95)
+        cx = rng.uniform(x_range[0], x_range[1])
         side = rng.choice([-1.0, 1.0])
         cy = side * rng.uniform(7.0, 38.0)
         yaw = rng.uniform(0, np.pi)
@@ -92,7 +92,7 @@ def make_world(seed: int, n_walls: int = 60, n_poles: int = 40) -> World:
             y0, y1 = min(y0, -6.0), min(y1, -6.0)
         walls[i] = (cx - dx, y0, cx + dx, y1, 0.0, rng.uniform(2.0, 5.0))
     poles = np.zeros((n_poles, 4))
-    poles[:, 0] = rng.uniform(-75, 95, n_poles)
+    poles[:, 0] = rng.uniform(x_range[0], x_range[1], n_poles)
     poles[:, 1] = rng.choice([-1.0, 1.0], n_poles) * rng.uniform(5.5, 30.0, n_poles)
     poles[:, 2] = rng.uniform(0.08, 0.2, n_poles)
     poles[:, 3] = rng.uniform(3.0, 6.0, n_poles)
@@ -348,6 +348,119 @@ def write_dataset(root: str, meta_dir: str, shape: Shape = LYFT, n_traversals: i
 
 
 # --------------------------------------------------------------------------------------------
+# In-memory track dataset (streaming engine, benchmarks): the same structure write_dataset puts
+# on disk -- several traversals of one road, every frame a valid query whose history is the
+# `history_frames` nearest frames of every traversal -- so that consecutive query scans share
+# their history frames the way real drives do.
+# --------------------------------------------------------------------------------------------
+@dataclass
+class TrackDataset:
+    shape: Shape
+    frames: dict                     # frame id -> (N,4) f32, the velodyne/%06d.bin content
+    poses: dict                      # frame id -> Pose
+    track_list: list                 # [[frame ids of traversal 0], ...]
+    valid_idx: dict                  # scan id -> (seq, pos, [(seq_id, [pos, ...]), ...])   (split_traintest.py:110-113)
+    calib: dict
+
+    @property
+    def scan_ids(self):
+        return list(self.valid_idx.keys())
+
+    def fixed_frame(self, scan_id):
+        """First frame of the first listed traversal (pre_compute_pp_score.py:127-130)."""
+        seq_id, positions = self.valid_idx[scan_id][2][0]
+        return self.track_list[seq_id][positions[0]]
+
+    def history_frames(self, scan_id):
+        """[[frame ids of traversal 0's history], ...] in the order the reference concatenates them."""
+        return [[self.track_list[seq_id][p] for p in positions] for seq_id, positions in self.valid_idx[scan_id][2]]
+
+    def relative_pose(self, scan_id, frame_id):
+        return relative_pose_f32(self.poses[self.fixed_frame(scan_id)], self.poses[frame_id], self.shape.nusc)
+
+    def relative_poses(self, scan_id, frame_ids):
+        """(n,4,4) f32, the bits of relative_pose(): the per-frame product ego @ l2e @ KITTI2NU is kept."""
+        cache = self.__dict__.setdefault("_chain", {})
+        k = kitti2nu(self.shape.nusc)
+        f64 = lambda a: a.astype(np.float32).astype(np.float64)
+        for f in frame_ids:
+            if f not in cache:
+                cache[f] = f64(self.poses[f].ego) @ f64(self.poses[f].l2e) @ k
+        fixed = self.poses[self.fixed_frame(scan_id)]
+        m = np.stack([cache[f] for f in frame_ids])
+        for lhs in (f64(fixed.ego), f64(fixed.l2e), k):
+            m = np.linalg.solve(lhs[None], m)
+        return m.astype(np.float32)
+
+
+def _track_frame(args):
+    world, pose, shape, fid, n_points = args
+    return fid, sample_frame(world, pose, shape, np.random.default_rng(SEED_BASE + fid), n_points=n_points)
+
+
+def make_track_dataset(shape: Shape = LYFT, n_traversals: int = 16, frames_per_traversal: int = 30,
+                       history_frames: int = 1, n_points=None, seed: int = SEED_BASE, first_frame_id: int = 0,
+                       workers: int = 0) -> TrackDataset:
+    """`n_traversals` passes over one straight road, a frame every 2 m.  Frame ids are traversal-major
+    starting at `first_frame_id`.  `workers` > 1 samples the frames in a process pool."""
+    span = 2.0 * frames_per_traversal
+    world = make_world(seed, n_walls=int(60 * (170.0 + span) / 170.0), n_poles=int(40 * (170.0 + span) / 170.0),
+                       x_range=(-75.0, 95.0 + span))
+    track_list, poses, todo = [], {}, []
+    fid = first_frame_id
+    tposes = []
+    for t in range(n_traversals):
+        rng = np.random.default_rng(seed + 7919 * (t + 1))
+        lateral, start = rng.uniform(-0.6, 0.6), rng.uniform(-1.0, 1.0)
+        track, tp = [], []
+        for k in range(frames_per_traversal):
+            pose = make_pose(start + 2.0 * k, lateral, np.deg2rad(rng.uniform(-2.0, 2.0)), shape, world)
+            poses[fid] = pose
+            todo.append((world, pose, shape, fid, n_points))
+            track.append(fid)
+            tp.append(pose)
+            fid += 1
+        track_list.append(track)
+        tposes.append(tp)
+    if workers and workers > 1:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(workers) as pool:
+            frames = dict(pool.map(_track_frame, todo, chunksize=max(1, len(todo) // (4 * workers))))
+    else:
+        frames = dict(_track_frame(a) for a in todo)
+    valid_idx = {}
+    for t in range(n_traversals):
+        for k in range(frames_per_traversal):
+            x = tposes[t][k].oxts[0]
+            hist = []
+            for u in [t] + [v for v in range(n_traversals) if v != t]:
+                xs = np.array([p.oxts[0] for p in tposes[u]])
+                order = [j for j in np.argsort(np.abs(xs - x), kind="stable") if not (u == t and j == k)]
+                hist.append((u, sorted(int(j) for j in order[:history_frames])))
+            valid_idx[track_list[t][k]] = (t, k, hist)
+    return TrackDataset(shape=shape, frames=frames, poses=poses, track_list=track_list, valid_idx=valid_idx,
+                        calib=default_calib(shape))
+
+
+def scan_case_from_dataset(ds: TrackDataset, scan_id: int) -> "ScanCase":
+    """The arrays pre_compute_pp_score.py holds for one query scan of the dataset at :188: query and
+    per-traversal history in the fixed frame (host arithmetic of the reference: transform_points)."""
+    hist = []
+    for fids in ds.history_frames(scan_id):
+        parts = []
+        for f in fids:
+            pts = ds.frames[f][:, :3]
+            if ds.shape.nusc:
+                m = (pts[:, 0] < 1.75) & (pts[:, 0] >= -1.15) & (pts[:, 1] < 0.65) & (pts[:, 1] >= -0.65)
+                pts = pts[~m]
+            parts.append(transform_points_f32(pts, ds.relative_pose(scan_id, f)))
+        hist.append(np.ascontiguousarray(np.concatenate(parts).astype(np.float32)))
+    q = ds.frames[scan_id]
+    qf = transform_points_f32(q[:, :3], ds.relative_pose(scan_id, scan_id))
+    return ScanCase(scan_id=scan_id, query=q, query_fixed=np.ascontiguousarray(qf), history=hist, calib=ds.calib)
+
+
+# --------------------------------------------------------------------------------------------
 # In-memory scans (benchmarks, kernel parity tests): query + T history clouds, all already in
 # the fixed frame, i.e. what pre_compute_pp_score.py holds at :188 just before the tree build.
 # --------------------------------------------------------------------------------------------
@@ -376,6 +489,17 @@ def relative_pose_f32(fixed: Pose, query: Pose, nusc: bool) -> np.ndarray:
     m = np.linalg.solve(fixed.ego.astype(np.float32).astype(np.float64), m)
     m = np.linalg.solve(fixed.l2e.astype(np.float32).astype(np.float64), m)
     return np.linalg.solve(k, m).astype(np.float32)
+
+
+def relative_poses_f32(fixed: Pose, queries: list, nusc: bool) -> np.ndarray:
+    """relative_pose_f32 for many query frames at once: (n,4,4) f32.  numpy's stacked solve runs the
+    same LAPACK gesv per matrix, so every result has the bits of the one-at-a-time call."""
+    k = kitti2nu(nusc)
+    f64 = lambda a: a.astype(np.float32).astype(np.float64)
+    m = np.stack([f64(q.ego) @ f64(q.l2e) @ k for q in queries])
+    for lhs in (f64(fixed.ego), f64(fixed.l2e), k):
+        m = np.linalg.solve(lhs[None], m)
+    return m.astype(np.float32)
 
 
 def make_scan_case(scan_id: int, shape: Shape = LYFT, n_traversals: int = 16,

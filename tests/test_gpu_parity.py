@@ -539,12 +539,41 @@ def test_knn_ties_beyond_k_keep_the_graph_symmetric_and_do_not_abort(golden_case
     assert all((j, i) in edges for (i, j) in edges)            # symmetric
     kept_pos = {int(o): i for i, o in enumerate(kept_idx.cpu().numpy()[:nk])}
     d = [kept_pos[int(i)] for i in dup]
-    assert all(cnt[i] > 0 for i in d)                           # the duplicates still find each other
+    # every duplicate keeps the same first k of its tied neighbours (as a k-nearest query that breaks
+    # ties by traversal order does), so those k + 1 are mutually connected and the rest are not
+    assert sum(cnt[i] >= k for i in d) >= k
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         r = p.run(b, rng="device", seed=1)
         p.check_flags(r)                                        # warns, does not raise
     assert any("ties" in str(x.message) for x in w)
+
+
+@pytest.mark.parametrize("shape_name", ["lyft", "nusc"])
+def test_engine_frame_jobs_match_host_batches(shape_name):
+    """SURVEY 8(f-2) in the engine: scans given as (frame ids, poses) with the raw frames in a
+    device cache and stage B on the GPU produce the label text of the same scans given as host
+    arrays the reference's host arithmetic transformed (pre_compute_pp_score.py:125-167); every
+    raw frame crosses PCIe exactly once."""
+    from modest_b200 import engine as eng, frames as fr, synth
+    shape = synth.NUSC if shape_name == "nusc" else synth.LYFT
+    ds = synth.make_track_dataset(shape, n_traversals=4, frames_per_traversal=3, history_frames=2 if shape.nusc else 1,
+                                  n_points=7000, seed=77)
+    ids = ds.scan_ids
+    cfg = dict(plane_estimate=dict(range=[[-70, 70], [-20, 20]], max_hs=shape.max_hs, offset=0.05),
+               image_shape=list(shape.image_shape))
+    e1 = eng.SeedLabelEngine(cfg, seed=9, frame_source=fr.pinned_frame_source(ds.frames))
+    got = {sid: t for b_ids, texts in e1.process(fr.jobs_from_dataset(ds, ids, 5)) for sid, t in zip(b_ids, texts)}
+    assert e1.frame_cache.misses == len(ds.frames) and e1.frame_cache.hits > 0
+    assert e1.frame_cache.h2d_bytes == sum(f.nbytes for f in ds.frames.values())
+    cases = [synth.scan_case_from_dataset(ds, sid) for sid in ids]
+    hbs = [eng.make_host_batch([c.query_fixed for c in cases[i:i + 4]], [c.history for c in cases[i:i + 4]],
+                               [c.query for c in cases[i:i + 4]], [c.calib for c in cases[i:i + 4]],
+                               scan_ids=ids[i:i + 4]) for i in range(0, len(ids), 4)]
+    e2 = eng.SeedLabelEngine(cfg, seed=9)
+    want = {sid: t for b_ids, texts in e2.process(hbs) for sid, t in zip(b_ids, texts)}
+    assert got == want
+    assert any(got.values())
 
 
 def test_engine_reports_overflowed_capacity(golden_case):
