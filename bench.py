@@ -3,24 +3,36 @@ PP-score + RANSAC + DBSCAN + NMS at 60k points).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A step = one pass of the whole hot path over one batch of synthetic Lyft-shaped scans
-(60 000 points, 16 historical traversals of one frame each): PP score -> RANSAC plane ->
+Workload: a synthetic Lyft-shaped drive -- 16 traversals of one road, a 60 000-point frame every
+2 m; every frame is a query scan whose history is the nearest frame of each of the 16 traversals
+(BASELINE "60k pts, 16 traversals", one frame per traversal).  K steps x 48 scans = K*48 DISTINCT
+scans per GPU, each processed once per timed loop.  A step = one pass of the whole hot path over
+one batch of 48 scans: stage B (frames into the scan's fixed frame) -> PP score -> RANSAC plane ->
 masks -> mutual-kNN graph -> DBSCAN -> second plane -> cluster gates -> box fit -> BEV NMS.
-`value` times the device work with the inputs resident in HBM (CUDA events, max over ranks);
-`e2e` times the public API with HOST inputs: pinned host -> device copies, the same kernels,
-device -> host copy of boxes / keep flags, KITTI label text (and, for N > 1, the one
-all-gather that collates the label blobs).  `roofline` is the PP neighbour-count kernel:
-algorithmic bytes (12 B per query point + 12 B per history point + 4 B per score) over its
-CUDA-event duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+
+`value`  device work with the inputs resident in HBM (all raw frames in the device frame cache),
+         CUDA events over the engine's lanes, max over ranks.
+`e2e`    the public streaming API (SeedLabelEngine.process on frames.JobBatch) from HOST data:
+         every raw frame is uploaded from pinned host memory inside the timed region (once: the
+         device cache keeps it for the later scans that share it), poses / job tables per batch,
+         device -> host copy of boxes / keep flags, KITTI label text; for N > 1 the one
+         all-gather that collates the label blobs.
+`roofline` the PP history pass (pp_count_kernel): algorithmic bytes (12 B per query point + 12 B
+         per history point + 4 B per score) over its CUDA-event duration, against the measured HBM
+         copy bandwidth in MEASURED_PEAKS.json.
+`nusc`   BASELINE config 5 in small: nuScenes-shaped drive (34k points, 16 traversals x 16 frames
+         of history per scan, max_hs=-1.3, centre removal), end to end incl. label files on disk.
 `--impl reference` times the reference's own CPU path (oracle port: SciPy cKDTree +
-scikit-learn, what the reference's programs call) on the host cores.
+scikit-learn, what the reference's programs call) on the host cores, on scans of the same drive.
 """
 import argparse
 import ctypes
 import json
+import math
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -35,7 +47,7 @@ N_POINTS, N_TRAV = 60000, 16
 # (425.8 MB read + 69.1 MB written); the kernel's traffic is proportional to the scans per launch
 PP_COUNT_DRAM_TRAFFIC_PER_SCAN = (425_806_080 + 69_080_320) / 24
 METRIC = "LiDAR scans/sec (PP-score+RANSAC+DBSCAN+NMS) @60k pts"
-WORKLOAD = "full seed-label pipeline, synthetic Lyft-shape scans (60k pts, 16 traversals x 1 frame)"
+WORKLOAD = "full seed-label pipeline, synthetic Lyft-shape drive (60k pts, 16 traversals x 1 frame of history per scan)"
 
 
 def hbm_peak():
@@ -93,15 +105,20 @@ def host_info():
             "sklearn": sklearn.__version__}
 
 
-def make_pool(n_scans, seed0):
+def drive(shape_name, n_scans, rank, world, history_frames=1, n_points=None, id_base=0):
+    """The synthetic drive of one rank: >= n_scans frames in 16 traversals (frame ids = scan ids)."""
     from modest_b200 import synth
-    return [synth.make_scan_case(seed0 + i, synth.LYFT, n_traversals=N_TRAV, frames_per_traversal=1,
-                                 n_points=N_POINTS) for i in range(n_scans)]
+    shape = synth.NUSC if shape_name == "nusc" else synth.LYFT
+    per = max(math.ceil(n_scans / N_TRAV), history_frames if history_frames > 1 else 2)
+    workers = max(1, min(16, (os.cpu_count() or 1) // max(world, 1)))
+    return synth.make_track_dataset(shape, n_traversals=N_TRAV, frames_per_traversal=per, history_frames=history_frames,
+                                    n_points=n_points, seed=1024 + 10007 * rank + (7 if shape.nusc else 0),
+                                    first_frame_id=rank * 10_000_000 + id_base, workers=workers)
 
 
 # ------------------------------------------------------------------------------------------------
 def cpu_one_scan(case):
-    """The reference's CPU path for one scan (oracle port), returns the label text."""
+    """The reference's CPU path for one scan (oracle port), returns the label text length."""
     from oracle import modest_oracle as orc
     pp = orc.pp_score(case.query_fixed, case.history)
     cal = orc.Calib(table=case.calib)
@@ -110,11 +127,20 @@ def cpu_one_scan(case):
     return len(text)
 
 
-def _cpu_worker(scan_id):
+_CPU_DRIVE = {}
+
+
+def _cpu_worker(k):
+    """One scan of a small drive (generated once per worker process, outside the timing): stage B on
+    the host (transform_points arithmetic), then the CPU path."""
     os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
     from modest_b200 import synth
-    case = synth.make_scan_case(scan_id, synth.LYFT, n_traversals=N_TRAV, frames_per_traversal=1, n_points=N_POINTS)
+    if "ds" not in _CPU_DRIVE:
+        _CPU_DRIVE["ds"] = synth.make_track_dataset(synth.LYFT, n_traversals=N_TRAV, frames_per_traversal=4, history_frames=1,
+                                                    n_points=N_POINTS, seed=500000)
+    ds = _CPU_DRIVE["ds"]
     t0 = time.perf_counter()
+    case = synth.scan_case_from_dataset(ds, ds.scan_ids[k % len(ds.scan_ids)])
     cpu_one_scan(case)
     return time.perf_counter() - t0
 
@@ -133,8 +159,7 @@ def run_reference(args):
     per_step = []
     with ctx.Pool(workers) as pool:
         for step in range(args.warmup + args.steps):
-            ids = [100000 + step * workers + w for w in range(workers)]
-            times = pool.map(_cpu_worker, ids)
+            times = pool.map(_cpu_worker, [step * workers + w for w in range(workers)], chunksize=1)
             if step >= args.warmup:
                 per_step.append(max(times))          # the step ends when its slowest worker ends
     total_t = float(sum(per_step))
@@ -144,7 +169,7 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": WORKLOAD, "scans_per_step": workers},
             "cpu_baseline": {"value": value, "unit": "scans/s", "cores": workers, "kind": "port",
-                             "sample": f"{workers} scans per step, one per process (cKDTree + sklearn, 1 thread each)",
+                             "sample": f"{workers} scans per step, one per process (transform_points + cKDTree + sklearn, 1 thread each)",
                              "host": host_info()},
             "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -156,8 +181,9 @@ def run_ours(args):
     import torch
     import torch.distributed as td
     from modest_b200 import _lib, dist
-    from modest_b200 import pipeline as pl
-    from modest_b200 import pp_score as pp_mod
+    from modest_b200 import engine as eng
+    from modest_b200 import frames as fr
+    from modest_b200 import synth
 
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -168,121 +194,96 @@ def run_ours(args):
         dist.init("nccl")
     lib = _lib.lib()
     B = args.scans_per_step
-    cases = make_pool(B, 1000 + 10007 * rank)
-
-    # ---- host-side (pinned) copies for the e2e path, device-resident copies for `value`
-    q_fixed = [torch.from_numpy(c.query_fixed).pin_memory() for c in cases]
-    hist = [[torch.from_numpy(h).pin_memory() for h in c.history] for c in cases]
-    ptc_host = [torch.from_numpy(c.query).pin_memory() for c in cases]
-    calibs = [c.calib for c in cases]
-    h2d_bytes = sum(t.numel() * 4 for t in q_fixed) + sum(t.numel() * 4 for h in hist for t in h) + \
-        sum(t.numel() * 4 for t in ptc_host)     # == host_batch.h2d_bytes
-
-    scorer = pp_mod.PPScorer()
-    pipe = pl.SeedLabelPipeline()
-    pp_batch = pp_mod.pack_batch(q_fixed, hist)
-    pp_out = torch.empty(pp_batch.n_query_total, dtype=torch.float32, device="cuda")
-    scan_batch = pl.make_batch(ptc_host, [torch.zeros(N_POINTS) for _ in cases], calibs)
-    scan_batch.pp = pp_out
-
-    # independent pipelines on their own streams: consecutive steps alternate between them so that
-    # the many one-CTA-per-scan kernels of one step overlap the wide kernels of the other
-    lanes = [(torch.cuda.Stream(), pp_mod.PPScorer(), pl.SeedLabelPipeline(),
-              torch.empty(pp_batch.n_query_total, dtype=torch.float32, device="cuda")) for _ in range(args.streams)]
-    lane_batches = []
-    for (_, _, _, ppbuf) in lanes:
-        sbk = pl.make_batch(ptc_host, [torch.zeros(N_POINTS) for _ in cases], calibs)
-        sbk.pp = ppbuf
-        lane_batches.append(sbk)
-
-    def device_step(seed):
-        st, sc, pp_, ppbuf = lanes[seed % len(lanes)]
-        with torch.cuda.stream(st):
-            sc(pp_batch, out=ppbuf, stream=st)
-            return pp_.run(lane_batches[seed % len(lanes)], rng="device", seed=seed, stream=st)
-
-    from modest_b200 import engine as eng
-    host_batch = eng.make_host_batch([c.query_fixed for c in cases], [c.history for c in cases],
-                                     [c.query for c in cases], calibs, scan_ids=[rank * B + s for s in range(B)])
-    engine = eng.SeedLabelEngine()
-    d2h_bytes = [0]
-
-    def e2e_run(n_steps):
-        """The public streaming API: pinned host batches in, label text out; H2D of batch k+1
-        overlaps the kernels of batch k and the text formatting of batch k-1."""
-        n_lines = 0
-        blobs = {}
-        for k, (ids, texts) in enumerate(engine.process(host_batch for _ in range(n_steps))):
-            if world > 1:
-                blobs.update({k * world * B + i: t.encode() for i, t in zip(ids, texts)})   # scan ids are rank * B + s
-            n_lines += sum(t.count("\n") + 1 for t in texts if t)
-        if world > 1:       # the path's one collective: label files collated on rank 0 once per run
-            dist.gather_blobs(blobs)
-        d2h_bytes[0] = engine.d2h_bytes_last
-        return n_lines
+    t_gen = time.perf_counter()
+    ds = drive("lyft", args.steps * B, rank, world, n_points=N_POINTS)
+    warm = drive("lyft", B, rank, world, n_points=N_POINTS, id_base=5_000_000)
+    gen_s = time.perf_counter() - t_gen
+    scan_ids = ds.scan_ids[:args.steps * B]
+    source = fr.pinned_frame_source({**ds.frames, **warm.frames})
+    for f in list(ds.frames) + list(warm.frames):          # pin everything before any timing
+        source(f)
+    frame_bytes = sum(ds.frames[f].nbytes for f in ds.frames)
+    jobs = fr.jobs_from_dataset(ds, scan_ids, B)
+    warm_jobs = fr.jobs_from_dataset(warm, warm.scan_ids[:B], B)
 
     def barrier():
         if world > 1:
             td.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
+    # ------------------------------------------------------------------ device-resident `value`
+    engine = eng.SeedLabelEngine(frame_source=source, depth=args.streams - 1)
+    for f in list(ds.frames) + list(warm.frames):          # inputs resident in HBM: every raw frame cached
+        engine.frame_cache.get(f)
+    torch.cuda.synchronize()
+    slots = engine.slots[:args.streams]
+
+    def device_step(k, jb, slot_list):
+        slot = slot_list[k % len(slot_list)]
+        engine._upload_jobs(slot, jb)                      # job tables only (all frames are cached)
+        engine._compute(slot, k)
+        return slot
+
+    def timed_loop(batches, slot_list, per_step_events=False):
+        main = torch.cuda.current_stream()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps_ev = []
+        ev0.record(main)
+        engine.copy_stream.wait_event(ev0)
+        for sl in slot_list:
+            sl.stream.wait_event(ev0)
+        for k, jb in enumerate(batches):
+            if per_step_events:
+                a = torch.cuda.Event(enable_timing=True)
+                sl = slot_list[k % len(slot_list)]
+                a.record(sl.stream)
+            slot = device_step(k, jb, slot_list)
+            if per_step_events:
+                b_ = torch.cuda.Event(enable_timing=True)
+                b_.record(slot.stream)
+                steps_ev.append((a, b_))
+        for sl in slot_list:                     # the end event fires when every lane has drained
+            main.wait_event(sl.done)
+        ev1.record(main)
+        return ev0, ev1, steps_ev
+
     for w in range(max(args.warmup, 3)):
-        device_step(w)
+        device_step(w, warm_jobs[0], slots)
     barrier()
     assert lib.modest_pp_profile_enable(min(args.steps, 256)) == 0
-
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.modest_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    main_stream = torch.cuda.current_stream()
-    ev0.record(main_stream)
-    for st, *_ in lanes:
-        st.wait_event(ev0)
-    for k in range(args.steps):
-        res = device_step(100 + k)
-    for st, *_ in lanes:                     # the end event fires when every lane has drained
-        e = torch.cuda.Event()
-        e.record(st)
-        main_stream.wait_event(e)
-    ev1.record(main_stream)
+    ev0, ev1, steps_ev = timed_loop(jobs, slots, per_step_events=True)
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = lib.modest_launch_count() - launches0
     clocks = sampler.stop()
+    step_ms = sorted(a.elapsed_time(b_) for a, b_ in steps_ev)
     buf = (ctypes.c_float * 256)()
     n_prof = lib.modest_pp_profile_read(buf, 256)
     pp_ms_overlapped = float(np.mean([buf[i] for i in range(n_prof)])) if n_prof else float("nan")
+    n_boxes = int(slots[(len(jobs) - 1) % len(slots)].result.n_boxes.sum().item())
     # The roofline kernel on its own: in the loop above its launches share the SMs with the other
-    # lanes' kernels, which stretches every launch.  The same steps once more on ONE lane give
+    # lanes' kernels, which stretches every launch.  Some of the steps once more on ONE lane give
     # the kernel's own duration and a step it can be compared with (what the ncu launch list of
     # `--streams 1` shows as well); both durations are reported.
     k_single = min(args.steps, 8)
     assert lib.modest_pp_profile_enable(k_single) == 0
-    lanes_all, lanes[:] = list(lanes), lanes[:1]
-    device_step(0)
+    device_step(0, warm_jobs[0], slots[:1])
     barrier()
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record(main_stream)
-    lanes[0][0].wait_event(ev2)
-    for k in range(k_single):
-        device_step(200 + k)
-    e = torch.cuda.Event()
-    e.record(lanes[0][0])
-    main_stream.wait_event(e)
-    ev3.record(main_stream)
+    ev2, ev3, _ = timed_loop(jobs[:k_single], slots[:1])
     barrier()
     ms_single = ev2.elapsed_time(ev3) / k_single
     n_prof = lib.modest_pp_profile_read(buf, 256)
     pp_ms = float(np.mean([buf[i] for i in range(min(n_prof, k_single))])) if n_prof else float("nan")
     lib.modest_pp_profile_enable(0)
-    lanes[:] = lanes_all
-    n_boxes = int(res.n_boxes.sum().item())
+    pp_alg_bytes = slots[0].pp_batch.algorithmic_bytes
+    del engine, slots
+    torch.cuda.empty_cache()
 
-    # ---- e2e (host buffers in, label text out)
-    # raw pinned host -> device bandwidth of this box, for context next to the e2e number
+    # ------------------------------------------------------------------ e2e (host frames in, label text out)
     probe = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
     probe_d = torch.empty_like(probe, device="cuda")
     probe_d.copy_(probe, non_blocking=True)
@@ -293,14 +294,36 @@ def run_ours(args):
     torch.cuda.synchronize()
     h2d_gbs = 4 * probe.numel() * 4 / (time.perf_counter() - tp) / 1e9
     del probe, probe_d
-    e2e_run(max(args.warmup, 6))          # every slot of the engine's ring is touched before timing
+    engine = eng.SeedLabelEngine(frame_source=source)
+
+    def e2e_run(batches, collate):
+        """The public streaming API: job batches (frame ids + poses) in, label text out; frames the
+        device cache does not hold yet are uploaded from pinned host memory on the way."""
+        n_lines, blobs = 0, {}
+        for ids, texts in engine.process(batches):
+            if collate:
+                blobs.update({int(i): t.encode() for i, t in zip(ids, texts)})
+            n_lines += sum(t.count("\n") + 1 for t in texts if t)
+        if collate and world > 1:       # the path's one collective: label files collated on rank 0 once per run
+            dist.gather_blobs(blobs)
+        return n_lines
+
+    e2e_run((warm_jobs[0] for _ in range(max(args.warmup, 6))), False)     # every slot of the ring is touched
     barrier()
     engine.host_s.update(upload=0.0, launch=0.0, wait=0.0, text=0.0, batches=0)
+    h2d0 = engine.frame_cache.h2d_bytes + engine.h2d_bytes_tables
     t0 = time.perf_counter()
-    e2e_run(args.steps)
+    # the job batches (pose chains, job tables) are built inside the timed region, lazily
+    e2e_run((b for i in range(0, len(scan_ids), B) for b in fr.jobs_from_dataset(ds, scan_ids[i:i + B], B)), True)
     barrier()
     e2e_s = time.perf_counter() - t0
+    h2d_bytes = engine.frame_cache.h2d_bytes + engine.h2d_bytes_tables - h2d0
+    d2h_bytes = engine.d2h_bytes_last
     host_ms = {k: round(1e3 * v / max(engine.host_s["batches"], 1), 2) for k, v in engine.host_s.items() if k != "batches"}
+    del engine
+    torch.cuda.empty_cache()
+
+    nusc = None if args.no_nusc else run_nusc(args, rank, world, barrier)
 
     if world > 1:
         t = torch.tensor([ms, e2e_s * 1e3, pp_ms, ms_single, pp_ms_overlapped], dtype=torch.float64, device="cuda")
@@ -311,26 +334,31 @@ def run_ours(args):
         td.destroy_process_group()
     if rank != 0:
         return
-    total_scans = B * world * args.steps
+    total_scans = len(scan_ids) * world
     value = total_scans / (ms * 1e-3)
     peak, peak_src = hbm_peak()
-    alg_bytes = pp_batch.algorithmic_bytes
-    achieved = alg_bytes / (pp_ms * 1e-3) / 1e9
+    achieved = pp_alg_bytes / (pp_ms * 1e-3) / 1e9
+    pct = lambda p: step_ms[min(len(step_ms) - 1, int(p * len(step_ms)))]
     line = {
         "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "scans_per_step_per_gpu": B, "n_points": N_POINTS, "n_traversals": N_TRAV,
-                   "ransac": "device-drawn minimal sets, 100 trials scored, sklearn accept/early-stop replay",
-                   "l2": f"inputs larger than L2: {h2d_bytes / 1e6:.0f} MB touched per step",
-                   "streams": args.streams,
+                   "distinct_scans_per_gpu": len(scan_ids), "frames_per_gpu": len(ds.frames),
+                   "stages": "B (frame transform) + C..O",
+                   "ransac": "device-drawn minimal sets keyed by scan id, 100 trials scored, sklearn accept/early-stop replay",
+                   "l2": f"inputs larger than L2: {frame_bytes / 1e6:.0f} MB of raw frames, every step reads other frames and "
+                         f"writes {13.2 * B:.0f} MB of transformed points",
+                   "streams": args.streams, "step_ms_on_its_lane": {"p50": pct(0.5), "p95": pct(0.95), "max": step_ms[-1]},
                    "host_cpus": (f"{len(numa_cpus)} CPUs of the GPU's NUMA node" if numa_cpus else
                                  f"{len(os.sched_getaffinity(0))} (no NUMA binding: topology not exposed or already local)"),
-                   "boxes_last_step": n_boxes},
+                   "boxes_last_step": n_boxes, "dataset_generation_s": round(gen_s, 1)},
         "clocks": clocks,
-        "e2e": {"value": total_scans / e2e_s, "unit": "scans/s", "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": int(d2h_bytes[0]), "h2d_link_gbs_measured": round(h2d_gbs, 1),
-                "h2d_gbs_used": round(h2d_bytes * args.steps / e2e_s / 1e9, 1),
+        "e2e": {"value": total_scans / e2e_s, "unit": "scans/s", "h2d_bytes_per_step": int(h2d_bytes / args.steps),
+                "d2h_bytes_per_step": int(d2h_bytes), "h2d_link_gbs_measured": round(h2d_gbs, 1),
+                "h2d_gbs_used": round(h2d_bytes / e2e_s / 1e9, 2),
+                "what": "SeedLabelEngine.process(JobBatch): every raw frame uploaded once from pinned host memory inside the "
+                        "timed region and kept in the device frame cache, poses + job tables per batch, label text out",
                 "host_ms_per_batch": host_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "pp_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -338,23 +366,82 @@ def run_ours(args):
                      "traffic_source": "ncu --set full of a 24-scan launch (profiles/r1b_pp_count_bench_launch_ncu_full_summary.csv), "
                                        "scaled to this launch's scan count",
                      "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": pp_ms,
+                     "algorithmic_bytes_per_launch": int(pp_alg_bytes), "kernel_ms": pp_ms,
                      "share_of_step": pp_ms / ms_single,
                      "timed_on": f"{k_single} single-lane steps after the throughput loop ({ms_single:.3f} ms per step); "
                                  "in the overlapped loop the same launch lasts kernel_ms_overlapped",
                      "kernel_ms_overlapped": pp_ms_overlapped},
     }
+    if nusc is not None:
+        line["nusc"] = nusc
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
     if world == 1 and not args.no_cpu_baseline:
+        n_cpu = 3
         t0 = time.perf_counter()
-        cpu_one_scan(cases[0])
+        for k in range(n_cpu):
+            cpu_one_scan(synth.scan_case_from_dataset(ds, scan_ids[k * 7]))
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "scans/s", "cores": 1 if (os.cpu_count() or 1) == 1 else os.cpu_count(),
+        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "scans/s", "cores": os.cpu_count() or 1,
                                 "kind": "port",
-                                "sample": "1 scan of the same workload, one process: cKDTree single-threaded, "
-                                          "sklearn graph/DBSCAN with n_jobs=-1 as the reference calls them",
+                                "sample": f"{n_cpu} scans of the same drive, one process: transform_points, cKDTree "
+                                          "single-threaded, sklearn graph/DBSCAN with n_jobs=-1 as the reference calls them",
                                 "host": host_info()}
     print(json.dumps(line))
+
+
+def run_nusc(args, rank, world, barrier):
+    """BASELINE config 5 in small: nuScenes-shaped drive end to end through the engine, label files written."""
+    import torch
+    import torch.distributed as td
+    from modest_b200 import dist
+    from modest_b200 import engine as eng
+    from modest_b200 import frames as fr
+    from modest_b200 import synth
+    Bn, steps, F = 8, max(2, min(args.steps, 4)), 16
+    ds = drive("nusc", Bn * steps, rank, world, history_frames=F, id_base=2_000_000)
+    ids = ds.scan_ids[:Bn * steps]
+    source = fr.pinned_frame_source(ds.frames)
+    for f in ds.frames:
+        source(f)
+    cfg = dict(plane_estimate=dict(range=[[-70, 70], [-20, 20]], max_hs=synth.NUSC.max_hs, offset=0.05),
+               image_shape=list(synth.NUSC.image_shape))
+    engine = eng.SeedLabelEngine(cfg, frame_source=source)
+    warm_ids = ds.scan_ids[-Bn:]
+    list(engine.process(fr.jobs_from_dataset(ds, warm_ids, Bn) * 5))     # ring touched; the warm-up scans' frames get cached
+    engine.frame_cache.clear()
+    barrier()
+    h2d0 = engine.frame_cache.h2d_bytes + engine.h2d_bytes_tables
+    texts = {}
+    t0 = time.perf_counter()
+    for b_ids, tx in engine.process(b for i in range(0, len(ids), Bn) for b in fr.jobs_from_dataset(ds, ids[i:i + Bn], Bn)):
+        texts.update({int(i): t.encode() for i, t in zip(b_ids, tx)})
+    if world > 1:
+        texts = dist.gather_blobs(texts)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = engine.frame_cache.h2d_bytes + engine.h2d_bytes_tables - h2d0
+    t1 = time.perf_counter()
+    n_files = 0
+    if rank == 0:
+        with tempfile.TemporaryDirectory() as tmp:
+            out = os.path.join(tmp, "label_2")
+            os.makedirs(out)
+            for sid, blob in texts.items():
+                with open(os.path.join(out, f"{sid % 1000000:06d}.txt"), "wb") as fh:
+                    fh.write(blob)
+                n_files += 1
+    write_s = time.perf_counter() - t1
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    hist_pts = sum(ds.frames[f].shape[0] for g in ds.history_frames(ids[0]) for f in g)
+    return {"workload": "nuScenes-shape drive: 34k-pt scans, 16 traversals x 16 history frames per scan, max_hs=-1.3, "
+                        "centre removal on history frames, label files written",
+            "e2e": {"value": len(ids) * world / e2e_s, "unit": "scans/s", "scans": len(ids) * world,
+                    "h2d_bytes_per_scan": int(h2d / len(ids)), "history_points_per_scan": int(hist_pts)},
+            "label_files": {"written": n_files, "seconds": round(write_s, 4)},
+            "non_empty_labels": int(sum(1 for v in texts.values() if v))}
 
 
 def main():
@@ -365,7 +452,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scans-per-step", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=3, help="independent pipeline lanes for the device-resident loop")
+    ap.add_argument("--no-nusc", action="store_true", help="skip the nuScenes-shape secondary measurement")
+    ap.add_argument("--streams", type=int, default=3, help="pipeline lanes of the device-resident loop")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

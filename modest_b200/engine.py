@@ -206,8 +206,12 @@ class SeedLabelEngine:
             h_off = h_rows[first]                                                      # per traversal
             trav_off = np.concatenate([[0], np.cumsum(trav_counts)]).astype(np.int32)
             count_off = np.concatenate([[0], np.cumsum(qn * trav_counts)]).astype(np.int64)
-            crow = np.stack([pl.calib_row(c) for c in jb.calibs])
-            P2 = np.stack([pl.calib_P2(c) for c in jb.calibs])
+            memo = {}                                  # scans of one drive usually share one calibration object
+            for c in jb.calibs:
+                if id(c) not in memo:
+                    memo[id(c)] = (pl.calib_row(c), pl.calib_P2(c))
+            crow = np.stack([memo[id(c)][0] for c in jb.calibs])
+            P2 = np.stack([memo[id(c)][1] for c in jb.calibs])
             # job records: history -> hist buffer, query -> query buffer (both xyz in the fixed frame), raw scans -> ptc
             jobs = np.zeros(H + 2 * S, dtype=fr.FRAME_JOB)
             jobs["src"][:H] = [t.data_ptr() for t in h_t]

@@ -44,41 +44,55 @@ class JobBatch:
 
 
 class DeviceFrameCache:
-    """Raw frames resident on one GPU, bounded by `device_bytes`, LRU eviction.  `source(fid)` must
-    return the frame as a pinned (N,4) float32 host tensor (e.g. velodyne/%06d.bin read into pinned
-    memory); uploads are enqueued on the stream that is current when `get` is called."""
+    """Raw frames resident on one GPU.  `source(fid)` must return the frame as a pinned (N,4)
+    float32 host tensor (e.g. velodyne/%06d.bin read into pinned memory); uploads are enqueued
+    on the stream that is current when `get` is called.
 
-    def __init__(self, source, device_bytes=48 << 30):
-        self.source, self.device_bytes = source, int(device_bytes)
-        self._d, self._used = OrderedDict(), 0
+    Frames are packed into slabs of `slab_bytes` (one device allocation per slab, not per frame:
+    an allocation per 1 MB frame costs more host time than the whole batch's launches); when
+    `device_bytes` is exceeded the oldest slab is dropped with every frame in it."""
+
+    def __init__(self, source, device_bytes=48 << 30, slab_bytes=256 << 20):
+        self.source, self.device_bytes, self.slab_bytes = source, int(device_bytes), int(slab_bytes)
+        self._d = {}                      # fid -> (N,4) view into a slab
+        self._slabs = []                  # [tensor, used floats, [fids]] oldest first
         self.hits = self.misses = 0
         self.h2d_bytes = 0
 
     def __contains__(self, fid):
         return fid in self._d
 
+    def _room(self, n_floats):
+        if self._slabs and self._slabs[-1][1] + n_floats <= self._slabs[-1][0].numel():
+            return self._slabs[-1]
+        size = max(self.slab_bytes // 4, n_floats)
+        while self._slabs and 4 * (sum(sl[0].numel() for sl in self._slabs) + size) > self.device_bytes:
+            _, _, fids = self._slabs.pop(0)
+            for f in fids:
+                self._d.pop(f, None)
+        self._slabs.append([torch.empty(size, dtype=torch.float32, device="cuda"), 0, []])
+        return self._slabs[-1]
+
     def get(self, fid):
         t = self._d.get(fid)
         if t is not None:
-            self._d.move_to_end(fid)
             self.hits += 1
             return t
         self.misses += 1
         host = self.source(fid)
-        t = torch.empty(host.shape, dtype=torch.float32, device="cuda")
+        n = host.numel()
+        slab = self._room(n)
+        t = slab[0][slab[1]:slab[1] + n].view(host.shape)
+        slab[1] += (n + 3) // 4 * 4                     # frames stay 16-byte aligned
+        slab[2].append(fid)
         t.copy_(host, non_blocking=True)
-        nbytes = t.numel() * 4
-        self.h2d_bytes += nbytes
-        while self._d and self._used + nbytes > self.device_bytes:
-            _, old = self._d.popitem(last=False)
-            self._used -= old.numel() * 4
+        self.h2d_bytes += n * 4
         self._d[fid] = t
-        self._used += nbytes
         return t
 
     def clear(self):
         self._d.clear()
-        self._used = 0
+        self._slabs.clear()
 
 
 def pinned_frame_source(frames: dict):
@@ -106,20 +120,23 @@ def bin_file_source(velodyne_dir: str):
 
 def jobs_from_dataset(ds, scan_ids, batch_size) -> list:
     """JobBatches over `scan_ids` of a synth.TrackDataset, poses by the reference's pose chain
-    (synth.relative_pose_f32 restates pre_compute_pp_score.py:27-28)."""
+    (pre_compute_pp_score.py:27-28, three stacked solves per batch: TrackDataset.relative_poses_batch)."""
     out = []
     for i in range(0, len(scan_ids), batch_size):
         ids = list(scan_ids[i:i + batch_size])
-        q_T, h_fid, h_T, fpt = [], [], [], []
+        fpt, flat_scan, flat_fid = [], [], []
         for sid in ids:
             groups = ds.history_frames(sid)
             fpt.append([len(g) for g in groups])
-            flat = [f for g in groups for f in g]
-            poses = ds.relative_poses(sid, [sid] + flat)          # one stacked solve per scan
-            q_T.append(poses[0])
-            h_fid.extend(flat)
-            h_T.append(poses[1:])
-        out.append(JobBatch(scan_ids=ids, query_fid=np.array(ids, dtype=np.int64), query_T=np.stack(q_T).astype(np.float32),
-                            hist_fid=np.array(h_fid, dtype=np.int64), hist_T=np.concatenate(h_T).astype(np.float32),
+            flat_scan.append(sid)                                   # the query itself first, then its history
+            flat_fid.append(sid)
+            for g in groups:
+                flat_scan.extend([sid] * len(g))
+                flat_fid.extend(g)
+        poses = ds.relative_poses_batch(flat_scan, flat_fid)
+        is_q = np.zeros(len(flat_fid), dtype=bool)
+        is_q[np.cumsum([0] + [1 + sum(f) for f in fpt[:-1]])] = True
+        out.append(JobBatch(scan_ids=ids, query_fid=np.array(ids, dtype=np.int64), query_T=poses[is_q],
+                            hist_fid=np.array(flat_fid, dtype=np.int64)[~is_q], hist_T=poses[~is_q],
                             frames_per_trav=fpt, calibs=[ds.calib] * len(ids), remove_center=bool(ds.shape.nusc)))
     return out

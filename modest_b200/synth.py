@@ -22,6 +22,7 @@ Points are emitted beam-major / azimuth-minor like a spinning LiDAR's .bin file.
 """
 from __future__ import annotations
 
+import math
 import os
 import pickle
 from dataclasses import dataclass, field
@@ -125,6 +126,7 @@ def make_pose(x: float, y: float, yaw: float, shape: Shape, world: World) -> Pos
 def _sample_dynamic_boxes(rng, n_boxes):
     """Car-sized boxes in the SENSOR frame: (cx, cy, l, w, h, yaw). Never axis aligned."""
     out = np.zeros((n_boxes, 6))
+    centres = []
     k = 0
     tries = 0
     while k < n_boxes and tries < 10000:
@@ -135,9 +137,12 @@ def _sample_dynamic_boxes(rng, n_boxes):
             continue
         l, w, h = rng.uniform(3.5, 5.0), rng.uniform(1.6, 2.1), rng.uniform(1.4, 1.9)
         yaw = rng.uniform(0.12, np.pi / 2 - 0.12) + rng.integers(0, 2) * np.pi / 2
-        if k and np.min(np.hypot(out[:k, 0] - cx, out[:k, 1] - cy)) < 7.5:
+        # (plain-python distance test: same decisions as np.min(np.hypot(...)) < 7.5 without ~10k
+        #  numpy calls per frame -- the rejection loop usually runs to its try limit)
+        if any(math.hypot(px - cx, py - cy) < 7.5 for px, py in centres):
             continue
         out[k] = (cx, cy, l, w, h, yaw)
+        centres.append((cx, cy))
         k += 1
     return out[:k]
 
@@ -377,6 +382,26 @@ class TrackDataset:
 
     def relative_pose(self, scan_id, frame_id):
         return relative_pose_f32(self.poses[self.fixed_frame(scan_id)], self.poses[frame_id], self.shape.nusc)
+
+    def relative_poses_batch(self, scan_ids, frame_ids):
+        """(n,4,4) f32: pose of frame_ids[i] in the fixed frame of scan_ids[i], the bits of
+        relative_pose() (numpy's stacked solve runs LAPACK gesv per matrix, like the single calls)."""
+        chain = self.__dict__.setdefault("_chain", {})
+        fixed = self.__dict__.setdefault("_fixed", {})
+        k = kitti2nu(self.shape.nusc)
+        f64 = lambda a: a.astype(np.float32).astype(np.float64)
+        for f in frame_ids:
+            if f not in chain:
+                chain[f] = f64(self.poses[f].ego) @ f64(self.poses[f].l2e) @ k
+        for sid in scan_ids:
+            if sid not in fixed:
+                p = self.poses[self.fixed_frame(sid)]
+                fixed[sid] = (f64(p.ego), f64(p.l2e))
+        m = np.stack([chain[f] for f in frame_ids])
+        m = np.linalg.solve(np.stack([fixed[sid][0] for sid in scan_ids]), m)
+        m = np.linalg.solve(np.stack([fixed[sid][1] for sid in scan_ids]), m)
+        m = np.linalg.solve(k[None], m)
+        return m.astype(np.float32)
 
     def relative_poses(self, scan_id, frame_ids):
         """(n,4,4) f32, the bits of relative_pose(): the per-frame product ego @ l2e @ KITTI2NU is kept."""
