@@ -78,7 +78,20 @@ __device__ __forceinline__ void corners_of(const float* b, P2* c /*[5]*/) {
   c[0] = P2{x1, y1}; c[1] = P2{x2, y1}; c[2] = P2{x2, y2}; c[3] = P2{x1, y2};
 }
 
-__device__ float overlap_area(const float* box_a, const float* box_b) {
+// Boxes whose circumscribed circles are clearly apart share no point: overlap_area would build an
+// empty intersection polygon and return +0 (5 cm of slack covers the 1e-2 margin of inside_box and
+// any float32 rounding; NaNs compare false and take the full path).  Kept OUT of overlap_area and
+// that function out of line, so that its float32 code -- which has to reproduce the reference
+// kernel's bits -- does not depend on what surrounds the call.
+__device__ __forceinline__ bool clearly_apart(const float* box_a, const float* box_b) {
+  const float dx = box_a[0] - box_b[0], dy = box_a[1] - box_b[1];
+  const float ra = 0.5f * sqrtf(box_a[3] * box_a[3] + box_a[4] * box_a[4]);
+  const float rb = 0.5f * sqrtf(box_b[3] * box_b[3] + box_b[4] * box_b[4]);
+  const float rs = ra + rb + 0.05f;
+  return dx * dx + dy * dy > 1.001f * rs * rs;
+}
+
+__device__ __noinline__ float overlap_area_full(const float* box_a, const float* box_b) {
   const float a_angle = box_a[6], b_angle = box_b[6];
   P2 ca[5], cb[5];
   corners_of(box_a, ca);
@@ -129,6 +142,10 @@ __device__ float overlap_area(const float* box_a, const float* box_b) {
     area += cross2(u, v);
   }
   return fabs(area) / 2.0;
+}
+
+__device__ __forceinline__ float overlap_area(const float* a, const float* b) {
+  return clearly_apart(a, b) ? 0.f : overlap_area_full(a, b);
 }
 
 __device__ __forceinline__ float iou(const float* a, const float* b) {
