@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(256) box_center32_kernel(
   const int s = blockIdx.z, rank = blockIdx.y;
   if (rank >= min(n_valid[s], max_valid)) return;
   const int c = valid_list[(size_t)s * max_valid + rank];
+  if (stats[(size_t)s * max_clusters + c].valid != 1) return;        // certified to fail the volume gate: not fitted
   const int n = stats[(size_t)s * max_clusters + c].count;
   const int64_t mbase = off[s] + cl_off[(size_t)s * (max_clusters + 1) + c];
   const int32_t* mem = members + mbase;
@@ -299,6 +300,116 @@ __global__ void __launch_bounds__(256) box_center32_kernel(
   }
 }
 
+// ---- L.-1 clusters that cannot pass the volume gate are not fitted at all -------------------------
+// A few clusters per scan are huge (strips of ground beyond plane_estimate.range, long walls:
+// thousands of points) and are thrown away by the volume gate of generate_mask.py:95 after the
+// 901-heading search, which they dominate.  This kernel certifies "volume > max_volume" from
+// three facts that hold for EVERY heading the search could choose, so the search is skipped
+// without changing any result:
+//   * a rectangle that contains a triangle has at least twice its area, so the footprint area is
+//     >= |AB| * dist(C, AB) for any three cluster points A, B, C (here: the farthest pair of the
+//     four axis-extreme points and the point farthest from their line);
+//   * a point with cluster points in all four open quadrants around it (1 mm margin) lies inside
+//     their convex hull, hence strictly inside every rectangle that contains the cluster, hence
+//     inside the footprint test of get_lowest_point_rect: bottom >= its y, h >= y - ymin;
+//   * volume = area * h.
+// ClusterStat::valid becomes 2 for a certified cluster: still valid for filter_labels' output,
+// skipped by the fit, dropped by the finalize step exactly as the gate would drop it.
+struct ArgD { double v; int i; };
+__device__ __forceinline__ ArgD block_argmax(double v, int i, ArgD* sh /*[32]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = ArgD{v, i};
+  __syncthreads();
+  ArgD r = sh[0];
+  for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+    if (sh[k].v > r.v || (sh[k].v == r.v && sh[k].i < r.i)) r = sh[k];
+  return r;
+}
+
+__global__ void __launch_bounds__(256) box_prereject_kernel(
+    const int64_t* __restrict__ off, const double* __restrict__ rect, int max_clusters, ClusterStat* __restrict__ stats,
+    const int32_t* __restrict__ cl_off, const int32_t* __restrict__ members, const int32_t* __restrict__ n_valid,
+    const int32_t* __restrict__ valid_list, int max_valid, double max_volume) {
+  const int s = blockIdx.y, rank = blockIdx.x;
+  if (rank >= min(n_valid[s], max_valid)) return;
+  const int c = valid_list[(size_t)s * max_valid + rank];
+  ClusterStat* st = stats + (size_t)s * max_clusters + c;
+  const int n = st->count;
+  if (n < 64 || !(max_volume > 0.0) || max_volume > 1e200) return;     // small clusters are cheap to fit
+  const int32_t* mem = members + off[s] + cl_off[(size_t)s * (max_clusters + 1) + c];
+  const double* R = rect + 3 * off[s];
+  __shared__ ArgD sh[32];
+  const double kNegInf = -1e300;
+  // axis-extreme points and the y range
+  double kx0 = kNegInf, kx1 = kNegInf, kz0 = kNegInf, kz1 = kNegInf, ky0 = kNegInf, ky1 = kNegInf;
+  int ix0 = 0, ix1 = 0, iz0 = 0, iz1 = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int m = mem[i];
+    const double x = R[3 * m], y = R[3 * m + 1], z = R[3 * m + 2];
+    if (-x > kx0) { kx0 = -x; ix0 = m; }
+    if (x > kx1) { kx1 = x; ix1 = m; }
+    if (-z > kz0) { kz0 = -z; iz0 = m; }
+    if (z > kz1) { kz1 = z; iz1 = m; }
+    ky0 = fmax(ky0, -y); ky1 = fmax(ky1, y);
+  }
+  const ArgD ax0 = block_argmax(kx0, ix0, sh), ax1 = block_argmax(kx1, ix1, sh);
+  const ArgD az0 = block_argmax(kz0, iz0, sh), az1 = block_argmax(kz1, iz1, sh);
+  const double ymin = -block_argmax(ky0, 0, sh).v, ymax = block_argmax(ky1, 0, sh).v;
+  const int ext[4] = {ax0.i, ax1.i, az0.i, az1.i};
+  double best = -1.0, Ax = 0, Az = 0, Bx = 0, Bz = 0;
+  for (int a = 0; a < 4; ++a)
+    for (int b = a + 1; b < 4; ++b) {
+      const double dx = R[3 * ext[a]] - R[3 * ext[b]], dz = R[3 * ext[a] + 2] - R[3 * ext[b] + 2];
+      const double d2 = dx * dx + dz * dz;
+      if (d2 > best) { best = d2; Ax = R[3 * ext[a]]; Az = R[3 * ext[a] + 2]; Bx = R[3 * ext[b]]; Bz = R[3 * ext[b] + 2]; }
+    }
+  if (!(best > 0.0)) return;
+  // |AB| * dist(C, AB) = max |cross(B - A, C - A)|
+  double kc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int m = mem[i];
+    kc = fmax(kc, fabs((Bx - Ax) * (R[3 * m + 2] - Az) - (Bz - Az) * (R[3 * m] - Ax)));
+  }
+  const double area_lb = block_argmax(kc, 0, sh).v * (1.0 - 1e-9);
+  if (!(area_lb > 0.0)) return;
+  const double h_need = max_volume / area_lb * (1.0 + 1e-6) + 1e-9;
+  if (!(ymax - ymin > h_need)) return;                                // block-uniform
+  // among the points low enough, the one nearest the middle of the cluster is the likeliest interior point
+  const double cx = 0.5 * (ax1.v - ax0.v), cz = 0.5 * (az1.v - az0.v);
+  const double ex = fmax(ax1.v + ax0.v, 1e-9), ez = fmax(az1.v + az0.v, 1e-9);
+  double kp = kNegInf;
+  int ip = -1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int m = mem[i];
+    if (R[3 * m + 1] - ymin > h_need) {
+      const double d = -(fabs(R[3 * m] - cx) / ex + fabs(R[3 * m + 2] - cz) / ez);
+      if (d > kp) { kp = d; ip = m; }
+    }
+  }
+  const ArgD cand = block_argmax(kp, ip < 0 ? 0x7fffffff : ip, sh);
+  if (!(cand.v > kNegInf)) return;
+  const double px = R[3 * cand.i], pz = R[3 * cand.i + 2], delta = 1e-3;
+  int q = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int m = mem[i];
+    const double x = R[3 * m], z = R[3 * m + 2];
+    if (x > px + delta && z > pz + delta) q |= 1;
+    if (x < px - delta && z > pz + delta) q |= 2;
+    if (x < px - delta && z < pz - delta) q |= 4;
+    if (x > px + delta && z < pz - delta) q |= 8;
+  }
+  // (__syncthreads_or tells whether ANY thread's predicate is non-zero: one call per quadrant)
+  const int q1 = __syncthreads_or(q & 1), q2 = __syncthreads_or(q & 2), q3 = __syncthreads_or(q & 4), q4 = __syncthreads_or(q & 8);
+  if (q1 && q2 && q3 && q4 && threadIdx.x == 0) st->valid = 2;
+}
+
 // grid (kAngleChunks, valid-cluster rank, scan); each warp scores a strided subset of the chunk
 __global__ void __launch_bounds__(256) box_beta32_kernel(
     const int64_t* __restrict__ off, int max_clusters, const ClusterStat* __restrict__ stats, const int32_t* __restrict__ cl_off,
@@ -307,6 +418,7 @@ __global__ void __launch_bounds__(256) box_beta32_kernel(
   const int s = blockIdx.z, rank = blockIdx.y;
   if (rank >= min(n_valid[s], max_valid)) return;
   const int c = valid_list[(size_t)s * max_valid + rank];
+  if (stats[(size_t)s * max_clusters + c].valid != 1) return;        // certified to fail the volume gate: not fitted
   const int n = stats[(size_t)s * max_clusters + c].count;
   const float2* __restrict__ pts = xz32 + off[s] + cl_off[(size_t)s * (max_clusters + 1) + c];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -356,7 +468,7 @@ __global__ void __launch_bounds__(kFitThreads) box_fit_kernel(
   for (int c = blockIdx.x; c < C; c += gridDim.x) {
     const ClusterStat* st = stats + (size_t)s * max_clusters + c;
     BoxRec* bx = boxes + (size_t)s * max_clusters + c;
-    if (!st->valid) { if (threadIdx.x == 0) bx->keep = 0; continue; }
+    if (st->valid != 1) { if (threadIdx.x == 0) bx->keep = 0; continue; }   // invalid, or certified to fail the volume gate
     const int n = st->count;
     const int32_t* mem = members + off[s] + cl_off[(size_t)s * (max_clusters + 1) + c];
     const double* R = rect + 3 * off[s];
@@ -521,7 +633,7 @@ __global__ void __launch_bounds__(256) box_bottom_kernel(
     if (threadIdx.x == 0) nfeet = 0;
     __syncthreads();
     for (int c = c0 + threadIdx.x; c < min(C, c0 + kFootCap); c += blockDim.x) {
-      if (stats[(size_t)s * max_clusters + c].valid) {
+      if (stats[(size_t)s * max_clusters + c].valid == 1) {
         const BoxRec& b = boxes[(size_t)s * max_clusters + c];
         const int k = atomicAdd(&nfeet, 1);
         feet[k] = Foot{b.t[0], b.t[2], b.cosr, b.sinr, __ddiv_rn(b.l, 2.0), __ddiv_rn(b.w, 2.0), c, 0};
@@ -565,6 +677,7 @@ __global__ void box_finalize_kernel(const int64_t* __restrict__ off, int max_clu
   for (int c = 0; c < C; ++c) {
     if (!stats[(size_t)s * max_clusters + c].valid) continue;
     BoxRec& b = boxes[(size_t)s * max_clusters + c];
+    if (stats[(size_t)s * max_clusters + c].valid == 2) { b.keep = 0; continue; }   // volume certified > max_volume
     if (new_id[(size_t)s * max_clusters + c] <= 0) { b.keep = 0; continue; }   // id 0 is background for generate_mask.py:93
     const unsigned long long bo = bottom[(size_t)s * max_clusters + c];
     if (bo == 0ull) { b.keep = 0; atomicOr(flags, 8); continue; }      // empty footprint (reference would raise)
@@ -762,6 +875,9 @@ extern "C" int modest_filter_and_fit_batch(
   }
   MODEST_REQUIRE(n_angles <= kMaxAngles, "filter_and_fit: more than %d search angles", kMaxAngles);
   // beta32 rows are n_angles wide (n_angles <= kMaxAngles, the stride the workspace was sized for)
+  box_prereject_kernel<<<dim3(max_valid, n_scans), 256, 0, stream>>>(d_off, rect, max_clusters, stats, cl_off, members, d_n_valid,
+                                                                    valid_list, max_valid, vc.max_volume);
+  MODEST_LAUNCH_CHECK("box_prereject_kernel");
   box_center32_kernel<<<dim3(4, max_valid, n_scans), 256, 0, stream>>>(d_off, rect, max_clusters, stats, cl_off, members, d_n_valid,
                                                                       valid_list, max_valid, xz32);
   MODEST_LAUNCH_CHECK("box_center32_kernel");
@@ -779,7 +895,7 @@ extern "C" int modest_filter_and_fit_batch(
   MODEST_LAUNCH_CHECK("box_finalize_kernel");
   apply_final_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_labels_filtered, max_clusters, final_id, d_labels_final);
   MODEST_LAUNCH_CHECK("apply_final_kernel");
-  note_launch(14);
+  note_launch(15);
   return MODEST_OK;
 }
 
