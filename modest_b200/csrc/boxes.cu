@@ -806,6 +806,7 @@ extern "C" int modest_filter_and_fit_batch(
     int n_scans, int64_t n_points_total, int64_t max_points, int max_clusters, int max_boxes, const double* h_gates,
     const double* d_trig, const double* d_angles, int n_angles, int32_t* d_labels_filtered, int32_t* d_labels_final,
     double* d_boxes, int32_t* d_n_boxes, int32_t* d_n_valid, int32_t* d_flags, void* d_ws, size_t ws_bytes, void* stream_) {
+  modest::StageRange nvtx_("modest:J-M cluster gates + box fit");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scans <= 0) return MODEST_OK;
   MODEST_REQUIRE(d_ptc && d_off && d_pp && d_labels && d_n_clusters && d_planes && (d_calib || d_rect_in) && h_gates && d_trig &&
@@ -909,6 +910,7 @@ extern "C" int modest_box_pp_percentile_batch(const float* d_ptc, int point_stri
                                               const double* d_box_trig, const int32_t* d_n_boxes, int n_scans, int64_t n_points_total, int64_t max_points,
                                               int max_boxes, double q_f32, float* d_percentile, int32_t* d_count, void* d_ws,
                                               size_t ws_bytes, void* stream_) {
+  modest::StageRange nvtx_("modest:f-1 in-box PP percentile");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scans <= 0) return MODEST_OK;
   MODEST_REQUIRE(d_ptc && d_off && d_pp && (d_calib || d_rect_in) && d_boxes && d_n_boxes && d_percentile && d_count && d_ws,

@@ -1032,6 +1032,7 @@ extern "C" int modest_ground_mask_batch(const float* d_ptc, int point_stride, co
                                         const float* d_pp, const double* d_planes, int n_scans, double offset,
                                         const float* h_only_range, const float* h_limit_range, float* d_kept,
                                         int32_t* d_kept_idx, int32_t* d_n_kept, uint8_t* d_mask, void* stream_) {
+  modest::StageRange nvtx_("modest:F,G masks");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scans <= 0) return MODEST_OK;
   MODEST_REQUIRE(d_ptc && d_off && d_pp && d_planes && h_limit_range && d_kept && d_kept_idx && d_n_kept,
@@ -1074,6 +1075,7 @@ extern "C" int modest_affinity_graph_batch(const float* d_kept, const int64_t* d
                                            int n_neighbors, double radius, int grid_dim, int32_t* d_nbr,
                                            float* d_nbr_w, int32_t* d_nbr_cnt, double partition_eps, int32_t* d_nbr_eps_cnt, int32_t* d_flags, void* d_ws,
                                            size_t ws_bytes, void* stream_) {
+  modest::StageRange nvtx_("modest:H affinity graph");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scans <= 0 || n_points_total <= 0) return MODEST_OK;
   if (grid_dim <= 0) grid_dim = 288;
@@ -1162,6 +1164,7 @@ extern "C" int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept
                                    const int32_t* d_nbr, const float* d_nbr_w, const int32_t* d_nbr_cnt, const int32_t* d_nbr_eps_cnt, double eps,
                                    int min_samples, int32_t* d_labels_kept, int32_t* d_labels_full,
                                    int32_t* d_n_clusters, void* d_ws, size_t ws_bytes, void* stream_) {
+  modest::StageRange nvtx_("modest:I DBSCAN");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scans <= 0 || n_points_total <= 0) return MODEST_OK;
   MODEST_REQUIRE(d_off && d_n_kept && d_kept_idx && d_nbr && (d_nbr_w || d_nbr_eps_cnt) && d_nbr_cnt && d_labels_kept &&

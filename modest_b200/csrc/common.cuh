@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/modest_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -54,6 +56,13 @@ struct Arena {
 };
 
 int sm_count();
+
+// NVTX range over one stage's launch sequence (host side; free when no profiler listens): ncu /
+// nsys timelines show which reference stage (SURVEY.md 8(a) letter) a group of kernels belongs to.
+struct StageRange {
+  explicit StageRange(const char* name) { nvtxRangePushA(name); }
+  ~StageRange() { nvtxRangePop(); }
+};
 
 // ---- device helpers --------------------------------------------------------------------------
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }

@@ -340,6 +340,7 @@ extern "C" int modest_nms_normal(const float* d_boxes, int n, float thresh, int6
 
 extern "C" int modest_seed_nms_batch(const double* d_boxes, const int32_t* d_n_boxes, int n_scans, int max_boxes,
                                      float thresh, float* d_iou_or_null, float* d_iou_ws, uint8_t* d_keep, void* stream_) {
+  modest::StageRange nvtx_("modest:N seed NMS");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scans <= 0) return MODEST_OK;
   MODEST_REQUIRE(d_boxes && d_n_boxes && d_iou_ws && d_keep, "seed_nms: null pointer argument");

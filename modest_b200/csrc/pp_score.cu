@@ -1152,6 +1152,7 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
                                      float* d_pp, const int64_t* h_q_off, const int64_t* h_h_off,
                                      const int32_t* h_trav_off, int64_t group_points, int64_t bin_records,
                                      void* d_ws, size_t ws_bytes, void* stream_) {
+  modest::StageRange nvtx_("modest:C,D PP score");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (grid_dim <= 0) grid_dim = 512;
   MODEST_REQUIRE(n_scans >= 0 && n_trav_total >= 0, "pp_score: negative sizes");
@@ -1273,6 +1274,7 @@ extern "C" int modest_transform_frames_batch(const float* d_in, int point_stride
                                              const float* d_T, int n_frames, int64_t max_frame_points,
                                              int remove_center, const float* h_center_box, float* d_out,
                                              void* stream_) {
+  modest::StageRange nvtx_("modest:B frame transform");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_frames <= 0 || max_frame_points <= 0) return MODEST_OK;
   MODEST_REQUIRE(d_in && d_frame_off && d_T && d_out, "transform_frames: null pointer argument");
@@ -1293,6 +1295,7 @@ extern "C" int modest_transform_frames_batch(const float* d_in, int point_stride
 extern "C" int modest_transform_gather_batch(const void* d_jobs, int n_jobs, int src_stride, int out_stride,
                                              int64_t max_frame_points, const float* h_center_box, float* d_out,
                                              void* stream_) {
+  modest::StageRange nvtx_("modest:B frame transform (gather)");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_jobs <= 0 || max_frame_points <= 0) return MODEST_OK;
   static_assert(sizeof(FrameJob) == 96, "FrameJob is part of the ABI (96 bytes)");

@@ -488,6 +488,7 @@ extern "C" int modest_plane_candidates_batch(const float* d_ptc, int point_strid
                                              int n_scans, float max_hs, float x_lo, float x_hi, float y_lo,
                                              float y_hi, float* d_cand, int32_t* d_n_cand, float* d_thr,
                                              void* stream_) {
+  modest::StageRange nvtx_("modest:E plane candidates");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_scans <= 0) return MODEST_OK;
   MODEST_REQUIRE(d_ptc && d_off && d_cand && d_n_cand && d_thr, "plane_candidates: null pointer argument");
@@ -521,6 +522,7 @@ extern "C" int modest_ransac_fit_batch(const float* d_cand, const int64_t* d_off
                                        int max_trials, double* d_plane, double* d_model, int32_t* d_info,
                                        int32_t* d_triples_out, uint8_t* d_inlier_mask, void* d_ws,
                                        size_t ws_bytes, void* stream_) {
+  modest::StageRange nvtx_("modest:E RANSAC fit");
   if (n_scans <= 0) return MODEST_OK;
   const int rc = fit_args_ok(d_cand, d_off, d_n_cand, d_thr, d_plane, d_info, d_ws, n_scans, max_trials, ws_bytes);
   if (rc != MODEST_OK) return rc;
@@ -551,6 +553,7 @@ extern "C" int modest_road_plane_fit_batch(const double* d_cand, const int64_t* 
                                            const int32_t* d_triples, uint64_t seed, int max_trials,
                                            double* d_plane, int32_t* d_info, void* d_ws, size_t ws_bytes,
                                            void* stream_) {
+  modest::StageRange nvtx_("modest:f-3 road plane fit");
   if (n_scans <= 0) return MODEST_OK;
   const int rc = fit_args_ok(d_cand, d_off, d_n_cand, d_thr, d_plane, d_info, d_ws, n_scans, max_trials, ws_bytes);
   if (rc != MODEST_OK) return rc;
