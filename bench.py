@@ -294,7 +294,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     h2d_gbs = 4 * probe.numel() * 4 / (time.perf_counter() - tp) / 1e9
     del probe, probe_d
-    engine = eng.SeedLabelEngine(frame_source=source)
+    engine = eng.SeedLabelEngine(frame_source=source, depth=args.e2e_depth)
 
     def e2e_run(batches, collate):
         """The public streaming API: job batches (frame ids + poses) in, label text out; frames the
@@ -454,6 +454,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-nusc", action="store_true", help="skip the nuScenes-shape secondary measurement")
     ap.add_argument("--streams", type=int, default=3, help="pipeline lanes of the device-resident loop")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="batches the engine keeps computing while the host reads back an older one")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -576,6 +576,43 @@ def test_engine_frame_jobs_match_host_batches(shape_name):
     assert any(got.values())
 
 
+def test_nuscenes_shape_full_size_against_the_oracle():
+    """BASELINE config 5's shape at full size: 34 000-point nuScenes-shaped scans of a drive, history
+    of 3 traversals x 2 frames with the ego returns removed, plane_estimate.max_hs=-1.3, image
+    900x1600.  PP counts bit-exact against cKDTree, then the device-drawn pipeline against the
+    reference path replaying the same minimal sets (labels and label text identical)."""
+    from modest_b200 import synth
+    from oracle import modest_oracle as orc
+    shape = synth.NUSC
+    ds = synth.make_track_dataset(shape, n_traversals=3, frames_per_traversal=2, history_frames=2, seed=4242)
+    cases = [synth.scan_case_from_dataset(ds, sid) for sid in ds.scan_ids[:2]]
+    assert cases[0].query.shape[0] == 34000
+    cfg = dict(_cfg(shape), plane_estimate=dict(range=[[-70, 70], [-20, 20]], max_hs=-1.3, offset=0.05))
+    p = pl.SeedLabelPipeline(cfg)
+    pps = []
+    for c in cases:
+        pp, counts = pp_score.count_neighbors_and_score(c.query_fixed, c.history, return_counts=True)
+        ref_counts = orc.neighbor_counts(c.query_fixed, c.history)
+        assert np.array_equal(counts, ref_counts)
+        ref_pp = orc.persistence_entropy(ref_counts).astype(np.float32)
+        assert np.abs(pp - ref_pp).max() <= 1e-4
+        pps.append(ref_pp)
+    b = pl.make_batch([c.query for c in cases], pps, [c.calib for c in cases], scan_ids=[c.scan_id for c in cases])
+    r = p.run(b, rng="device", seed=21, want_debug=True)
+    p.check_flags(r)
+    texts = p.label_texts(b, r.boxes, r.n_boxes, r.keep)
+    tri1, tri2 = r.triples.cpu().numpy(), r.triples2.cpu().numpy()
+    ocfg = dict(orc.DEFAULT_MASK_CFG)
+    ocfg["plane_estimate"] = dict(ocfg["plane_estimate"], max_hs=-1.3)
+    for s, c in enumerate(cases):
+        cal = orc.Calib(table=c.calib)
+        ref_labels, objs = orc.seed_mask_for_scan(c.query, pps[s], cal, cfg=ocfg, draws=(tri1[s], tri2[s]))
+        assert np.array_equal(r.labels.cpu().numpy()[b.h_off[s]:b.h_off[s + 1]], ref_labels)
+        ref_text, _ = orc.labels_for_scan(objs, cal, lambda bx: orc.bev_iou_matrix_f32(bx, bx), image_shape=shape.image_shape)
+        assert texts[s] == ref_text
+    assert any(texts)
+
+
 def test_engine_reports_overflowed_capacity(golden_case):
     """The streaming engine reads the device capacity flags back with the boxes: a batch whose
     cluster table overflowed raises instead of turning truncated results into label text."""
