@@ -234,6 +234,49 @@ int modest_affinity_graph_batch(const float* d_kept, const int64_t* d_off,
                                 size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * the other rectangle fitters of get_obj() (utils/pointcloud_utils.py:88-165,
+ * 219-275) and get_lowest_point_rect() (:278-290), one cluster per call.
+ *   modest_fit_rectangle: d_xz (n,2) f64 rect (x,z) of the cluster; method 0 min_zx_area_fit
+ *     (minimum_bounding_rectangle), 1 PCA (PCA_rectangle), 2 variance_to_edge (variance_rectangle;
+ *     needs the search-angle tables of modest_filter_and_fit_batch and a workspace);
+ *     d_out 11 doubles: corners (4,2) row-major, angle, area, status (0 ok).
+ *   modest_lowest_point_rect: max rect-y of the rows of d_rect (n,3) strictly inside the footprint
+ *     centred (cx,cz) with half sizes l/2, w/2 rotated by ry (pass numpy's cos(ry), sin(ry));
+ *     *d_bottom = that y, NaN when no point is inside.
+ * ------------------------------------------------------------------------------------------ */
+size_t modest_fit_rectangle_workspace_bytes(int n, int n_angles);
+int modest_fit_rectangle(const double* d_xz, int n, int method, const double* d_trig,
+                         const double* d_angles, int n_angles, double* d_out, void* d_ws,
+                         size_t ws_bytes, void* stream);
+int modest_lowest_point_rect(const double* d_rect, int n, double cx, double cz, double cos_ry,
+                             double sin_ry, double l, double w, double* d_bottom, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * the non-default graph / affinity types of precompute_affinity_matrix()
+ * (utils/clustering_utils.py:16-31,49-56), one scan per call, exact brute force (these types are
+ * not on the seed-label path).
+ *   modest_knn_bruteforce: the n_neighbors nearest neighbours of every point at any distance
+ *     (sklearn kneighbors_graph: sequential f64 squared distances, self excluded);
+ *     d_knn (n, n_neighbors) i32, d_knn_cnt (n) i32 (= min(n_neighbors, n-1)), d_rk2 (n) f64 the
+ *     k-th squared distance; d2_max = an upper bound of every squared distance (bounding box);
+ *     *d_flags |= 2 when exact ties at the k-th distance were cut to the first k by index.
+ *   modest_radius_graph: radius_neighbors_graph (d2 <= radius^2, self excluded) in two calls:
+ *     counts (d_counts (n) i64, d_indices NULL), then -- after the caller's prefix sum -- the
+ *     fill (d_indptr (n+1) i64, d_indices i32, ascending within a row).
+ *   modest_edge_affinity: the float32 edge weights of :42-56 for a CSR pattern, widened to f64:
+ *     kind 0 'l1' |pp_r - pp_j|, 1 'exp' exp((pp_r - pp_j)^2), 2 '3d_l2_distance' the norm of the
+ *     difference of the first `width` columns of the point rows.
+ * ------------------------------------------------------------------------------------------ */
+int modest_knn_bruteforce(const float* d_pts, int point_stride, int n, int n_neighbors, double d2_max,
+                          int32_t* d_knn, int32_t* d_knn_cnt, double* d_rk2, int32_t* d_flags,
+                          void* stream);
+int modest_radius_graph(const float* d_pts, int point_stride, int n, double radius,
+                        int64_t* d_counts, const int64_t* d_indptr, int32_t* d_indices, void* stream);
+int modest_edge_affinity(const float* d_pts, int point_stride, int width, const float* d_pp,
+                         const int64_t* d_indptr, const int32_t* d_indices, int n, int kind,
+                         double* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stage I: DBSCAN on that graph.
  * Replaces sklearn.cluster.DBSCAN(metric='precomputed', eps, min_samples).fit(graph).labels_
  * (generate_mask.py:75-81): neighbourhood(i) = {j : edge, (double)w <= eps} + {i}; core iff

@@ -49,6 +49,12 @@ SIGNATURES = {
     "modest_graph_workspace_bytes": (_sz, [C.c_int, _i64, C.c_int, C.c_int]),
     "modest_affinity_graph_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, C.c_int, _f64, C.c_int,
                                               _vp, _vp, _vp, _f64, _vp, _vp, _vp, _sz, _vp]),
+    "modest_fit_rectangle_workspace_bytes": (_sz, [C.c_int, C.c_int]),
+    "modest_fit_rectangle": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _sz, _vp]),
+    "modest_lowest_point_rect": (C.c_int, [_vp, C.c_int, _f64, _f64, _f64, _f64, _f64, _f64, _vp, _vp]),
+    "modest_knn_bruteforce": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "modest_radius_graph": (C.c_int, [_vp, C.c_int, C.c_int, _f64, _vp, _vp, _vp, _vp]),
+    "modest_edge_affinity": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "modest_dbscan_workspace_bytes": (_sz, [_i64]),
     "modest_dbscan_batch": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, _f64,
                                       C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),

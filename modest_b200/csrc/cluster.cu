@@ -1024,6 +1024,103 @@ __global__ void __launch_bounds__(256) dbscan_merge_borders_kernel(
     if (!core[base + i]) labels_kept[base + i] = border_lab[base + i];
 }
 
+// ---- f-4: non-default graph types of precompute_affinity_matrix (clustering_utils.py:16-31) -----
+// 'knn' / 'sym_knn' / 'mutual_knn' need the exact k nearest neighbours at ANY distance and 'radius'
+// every pair within a radius; neither is on the seed-label path (the configs use
+// radius_mutual_knn), so they get exact brute-force kernels: one warp per point, every other
+// point of the scan evaluated in sklearn's sequential f64 arithmetic, the k-th distance by the
+// nested-histogram selection used above.
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_bruteforce_kernel(
+    const float* __restrict__ pts, int stride, int n, int k_nn, double d2_max, int32_t* __restrict__ knn,
+    int32_t* __restrict__ knn_cnt, double* __restrict__ rk2_out, int32_t* __restrict__ flags) {
+  __shared__ int hist_sh[kKnnWarps][kBins];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int* hist = hist_sh[wib];
+  const int kk = min(k_nn, n - 1);
+  for (int i = blockIdx.x * kKnnWarps + wib; i < n; i += gridDim.x * kKnnWarps) {
+    const float px = pts[(size_t)stride * i], py = pts[(size_t)stride * i + 1], pz = pts[(size_t)stride * i + 2];
+    auto scan_all = [&](auto f) {
+      for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        const bool live = j < n && j != i;
+        double d2 = 0.0;
+        if (live) d2 = sqdist_f64_seq(px, py, pz, pts[(size_t)stride * j], pts[(size_t)stride * j + 1], pts[(size_t)stride * j + 2]);
+        f(live, d2, j);
+      }
+    };
+    int emitted = 0;
+    double rk2 = 0.0;
+    if (kk > 0) {
+      kth_by_histogram<double>(scan_all, kk, d2_max, hist, lane, &rk2, flags);
+      int32_t* out = knn + (size_t)i * k_nn;
+      scan_all([&](bool live, double d2, int j) {
+        const bool in = live && d2 <= rk2;
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        const int slot = emitted + __popc(bal & ((1u << lane) - 1u));
+        if (in && slot < k_nn) out[slot] = j;
+        emitted += __popc(bal);
+      });
+    }
+    if (lane == 0) {
+      if (emitted > k_nn) { atomicOr(flags, 2); emitted = k_nn; }     // ties at the k-th distance: first k by index
+      knn_cnt[i] = emitted;
+      rk2_out[i] = rk2;
+    }
+    __syncwarp();
+  }
+}
+
+// FILL = false: counts[i] = neighbours of i within r2 (self excluded); FILL = true: their indices, ascending
+template <bool FILL>
+__global__ void __launch_bounds__(256) radius_bruteforce_kernel(const float* __restrict__ pts, int stride, int n, double r2,
+                                                                 int64_t* __restrict__ counts, const int64_t* __restrict__ indptr,
+                                                                 int32_t* __restrict__ indices) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < n; i += nwarps) {
+    const float px = pts[(size_t)stride * i], py = pts[(size_t)stride * i + 1], pz = pts[(size_t)stride * i + 2];
+    long long have = 0;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      const bool in = j < n && j != i &&
+                      sqdist_f64_seq(px, py, pz, pts[(size_t)stride * j], pts[(size_t)stride * j + 1], pts[(size_t)stride * j + 2]) <= r2;
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      if (FILL && in) indices[indptr[i] + have + __popc(bal & ((1u << lane) - 1u))] = j;
+      have += __popc(bal);
+    }
+    if (!FILL && lane == 0) counts[i] = have;
+  }
+}
+
+// edge weights of clustering_utils.py:42-56 for a CSR pattern, float32 arithmetic like numpy's:
+// kind 0 'l1' |pp_r - pp_j|, 1 'exp' exp((pp_r - pp_j)^2), 2 '3d_l2_distance' ||row_r - row_j|| over ALL
+// `width` columns of the point rows (the reference subtracts whole rows), summed left to right
+__global__ void __launch_bounds__(256) edge_affinity_kernel(const float* __restrict__ pts, int stride, int width,
+                                                            const float* __restrict__ pp, const int64_t* __restrict__ indptr,
+                                                            const int32_t* __restrict__ indices, int n, int kind,
+                                                            double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < n; i += nwarps) {
+    for (int64_t e = indptr[i] + lane; e < indptr[i + 1]; e += 32) {
+      const int j = indices[e];
+      float w;
+      if (kind == 2) {
+        float acc = 0.f;
+        for (int c = 0; c < width; ++c) {
+          const float d = __fsub_rn(pts[(size_t)stride * i + c], pts[(size_t)stride * j + c]);
+          acc = c == 0 ? __fmul_rn(d, d) : __fadd_rn(acc, __fmul_rn(d, d));
+        }
+        w = __fsqrt_rn(acc);
+      } else {
+        const float d = __fsub_rn(pp[i], pp[j]);
+        w = kind == 0 ? fabsf(d) : expf(__fmul_rn(d, d));
+      }
+      out[e] = (double)w;
+    }
+  }
+}
+
 }  // namespace modest
 
 using namespace modest;
@@ -1207,5 +1304,54 @@ extern "C" int modest_dbscan_batch(const int64_t* d_off, const int32_t* d_n_kept
   dbscan_merge_borders_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_n_kept, core, border_lab, d_labels_kept);
   MODEST_LAUNCH_CHECK("dbscan_merge_borders_kernel");
   note_launch(11);
+  return MODEST_OK;
+}
+
+extern "C" int modest_knn_bruteforce(const float* d_pts, int point_stride, int n, int n_neighbors, double d2_max,
+                                     int32_t* d_knn, int32_t* d_knn_cnt, double* d_rk2, int32_t* d_flags, void* stream_) {
+  modest::StageRange nvtx_("modest:f-4 exact kNN lists");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0) return MODEST_OK;
+  MODEST_REQUIRE(d_pts && d_knn && d_knn_cnt && d_rk2 && d_flags, "knn_bruteforce: null pointer argument");
+  MODEST_REQUIRE(point_stride >= 3 && n_neighbors >= 1 && d2_max > 0.0, "knn_bruteforce: bad arguments");
+  MODEST_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int32_t), stream));
+  int blocks = (n + kKnnWarps - 1) / kKnnWarps;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  knn_bruteforce_kernel<<<blocks, kKnnWarps * 32, 0, stream>>>(d_pts, point_stride, n, n_neighbors, d2_max, d_knn, d_knn_cnt,
+                                                              d_rk2, d_flags);
+  MODEST_LAUNCH_CHECK("knn_bruteforce_kernel");
+  note_launch(1);
+  return MODEST_OK;
+}
+
+extern "C" int modest_radius_graph(const float* d_pts, int point_stride, int n, double radius, int64_t* d_counts,
+                                   const int64_t* d_indptr, int32_t* d_indices, void* stream_) {
+  modest::StageRange nvtx_("modest:f-4 radius graph");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0) return MODEST_OK;
+  MODEST_REQUIRE(d_pts && point_stride >= 3 && radius >= 0.0, "radius_graph: bad arguments");
+  MODEST_REQUIRE((d_counts && !d_indices) || (d_indptr && d_indices), "radius_graph: pass d_counts (count call) or d_indptr + d_indices (fill call)");
+  int blocks = (n * 32 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const double r2 = radius * radius;
+  if (d_indices) radius_bruteforce_kernel<true><<<blocks, 256, 0, stream>>>(d_pts, point_stride, n, r2, nullptr, d_indptr, d_indices);
+  else radius_bruteforce_kernel<false><<<blocks, 256, 0, stream>>>(d_pts, point_stride, n, r2, d_counts, nullptr, nullptr);
+  MODEST_LAUNCH_CHECK("radius_bruteforce_kernel");
+  note_launch(1);
+  return MODEST_OK;
+}
+
+extern "C" int modest_edge_affinity(const float* d_pts, int point_stride, int width, const float* d_pp, const int64_t* d_indptr,
+                                    const int32_t* d_indices, int n, int kind, double* d_out, void* stream_) {
+  modest::StageRange nvtx_("modest:f-4 edge affinity");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n <= 0) return MODEST_OK;
+  MODEST_REQUIRE(d_indptr && d_indices && d_out && kind >= 0 && kind <= 2, "edge_affinity: bad arguments");
+  MODEST_REQUIRE(kind == 2 ? (d_pts && width >= 1 && width <= point_stride) : d_pp != nullptr, "edge_affinity: missing input for kind %d", kind);
+  int blocks = (n * 32 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  edge_affinity_kernel<<<blocks, 256, 0, stream>>>(d_pts, point_stride, width, d_pp, d_indptr, d_indices, n, kind, d_out);
+  MODEST_LAUNCH_CHECK("edge_affinity_kernel");
+  note_launch(1);
   return MODEST_OK;
 }

@@ -100,16 +100,49 @@ def distance_to_plane(ptc, plane, directional=False):
     return (d / torch.sqrt((pl[:3] ** 2).sum())).cpu().numpy()
 
 
+_FIT_METHOD_IDS = {'min_zx_area_fit': 0, 'PCA': 1, 'variance_to_edge': 2}
+
+
+def _fit_rectangle(points, method):
+    """(corners (4,2), angle, area) from modest_fit_rectangle; points (n,2) f64."""
+    xz = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
+    n = xz.shape[0]
+    if n < 1:
+        raise ValueError("empty cluster")
+    lib = _lib.lib()
+    pipe = _pipe()
+    trig, ang, n_ang = pipe._angle_tables("cuda")
+    xz_d = torch.from_numpy(xz).cuda()
+    out = torch.zeros(11, dtype=torch.float64, device="cuda")
+    need = int(lib.modest_fit_rectangle_workspace_bytes(n, n_ang))
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.modest_fit_rectangle(_lib.ptr(xz_d), n, _FIT_METHOD_IDS[method], _lib.ptr(trig), _lib.ptr(ang), n_ang,
+                                        _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "modest_fit_rectangle")
+    o = out.cpu().numpy()
+    if o[10] != 0.0:
+        raise ValueError("rectangle fit failed (status %g)" % o[10])
+    return o[:8].reshape(4, 2).copy(), np.float64(o[8]), np.float64(o[9])
+
+
 def minimum_bounding_rectangle(points):
-    raise NotImplementedError("min_zx_area_fit is not implemented on the GPU path (pointcloud_utils.py:88-146)")
+    """pointcloud_utils.py:88-146 -- smallest bounding rectangle with a side on a convex-hull edge.
+    Every hull edge is tried; the reference skips the edge that closes scipy's vertex list (whose
+    start is a qhull internal), so its rectangle can be marginally larger in that one case."""
+    return _fit_rectangle(points, 'min_zx_area_fit')
 
 
 def PCA_rectangle(cluster_ptc):
-    raise NotImplementedError("PCA fit is not implemented on the GPU path (pointcloud_utils.py:148-165)")
+    """pointcloud_utils.py:148-165 -- bounding rectangle along the principal axes (sklearn PCA's
+    sign convention); equal to sklearn's to rounding."""
+    return _fit_rectangle(cluster_ptc, 'PCA')
 
 
 def variance_rectangle(cluster_ptc, delta=0.1):
-    raise NotImplementedError("variance_to_edge is not implemented on the GPU path (pointcloud_utils.py:219-275)")
+    """pointcloud_utils.py:219-275 -- heading that minimises the variance of the distances to the
+    nearer edge, 901 headings, numpy's np.var arithmetic."""
+    if delta != 0.1:
+        raise NotImplementedError("variance_rectangle: only delta=0.1")
+    return _fit_rectangle(cluster_ptc, 'variance_to_edge')
 
 
 def _fit_single(cluster_rect, full_rect):
@@ -149,16 +182,40 @@ def closeness_rectangle(cluster_ptc, delta=0.1, d0=1e-2):
 
 
 def get_lowest_point_rect(ptc, xz_center, l, w, ry):
-    raise NotImplementedError("get_lowest_point_rect is fused into get_obj on the GPU path")
+    """pointcloud_utils.py:278-290 -- largest rect-y among the points strictly inside the footprint."""
+    rect = np.ascontiguousarray(np.asarray(ptc, dtype=np.float64)[:, :3])
+    rect_d = torch.from_numpy(rect).cuda()
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().modest_lowest_point_rect(_lib.ptr(rect_d), int(rect.shape[0]), float(xz_center[0]), float(xz_center[1]),
+                                                   float(np.cos(ry)), float(np.sin(ry)), float(l), float(w), _lib.ptr(out),
+                                                   _lib.stream_ptr()), "modest_lowest_point_rect")
+    bottom = float(out.cpu()[0])
+    if np.isnan(bottom):
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")   # ys.max() of nothing
+    return np.float64(bottom)
 
 
 def get_obj(ptc, full_ptc, fit_method='min_zx_area_fit'):
     """pointcloud_utils.py:292-317 -- box namespace (t, l, w, h, ry, volume) for one cluster given
-    in rect coordinates; only fit_method='closeness_to_edge' exists on the GPU."""
-    if fit_method != 'closeness_to_edge':
+    in rect coordinates.  'closeness_to_edge' (the configured method) runs the fused seed-label
+    kernels; the other three fitters run the operator-level kernels of csrc/fitters.cu and the
+    scalar assembly of :303-316."""
+    if fit_method == 'closeness_to_edge':
+        return box_namespace(_fit_single(ptc, full_ptc))
+    if fit_method not in _FIT_METHOD_IDS:
         raise NotImplementedError(fit_method)
-    row = _fit_single(ptc, full_ptc)
-    return box_namespace(row)
+    ptc = np.asarray(ptc, dtype=np.float64)
+    corners, ry, area = _fit_rectangle(ptc[:, [0, 2]], fit_method)
+    ry = ry * -1
+    l = np.linalg.norm(corners[0] - corners[1])
+    w = np.linalg.norm(corners[0] - corners[-1])
+    c = (corners[0] + corners[2]) / 2
+    bottom = get_lowest_point_rect(full_ptc, c, l, w, ry)
+    h = bottom - ptc[:, 1].min()
+    obj = types.SimpleNamespace()
+    obj.t = np.array([c[0], bottom, c[1]])
+    obj.l, obj.w, obj.h, obj.ry, obj.volume = l, w, h, ry, area * h
+    return obj
 
 
 def box_namespace(row):

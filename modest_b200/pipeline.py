@@ -174,9 +174,10 @@ class SeedLabelPipeline:
         self.cfg = base
         g = self.cfg["graph"]
         if g["neighbor_type"] != "radius_mutual_knn" or g["affinity_type"] != "l1":
-            # utils/clustering_utils.py:16-31,49-56 has other branches; only the configured
-            # default is implemented on the GPU and there is no CPU fallback
-            raise NotImplementedError(f"{g['neighbor_type']}/{g['affinity_type']}")
+            # utils/clustering_utils.py:16-31,49-56 has other branches: the operator module
+            # (generate_cluster_mask/utils/clustering_utils.py) implements them, the fused batched
+            # pipeline only the configured default
+            raise NotImplementedError(f"{g['neighbor_type']}/{g['affinity_type']} in the fused pipeline")
         if self.cfg["clustering"]["method"] != "DBSCAN":
             raise NotImplementedError(self.cfg["clustering"]["method"])    # generate_mask.py:82-83
         if self.cfg["bbox_gen"]["fit_method"] != "closeness_to_edge":

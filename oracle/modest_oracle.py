@@ -310,6 +310,45 @@ def affinity_graph(ptc, pp, n_neighbors=70, radius=2.0):
     return scipy.sparse.csr_matrix((w.astype(np.float64), g.indices, g.indptr), shape=g.shape)
 
 
+def affinity_graph_variant(ptc, pp, neighbor_type, affinity_type, n_neighbors=70, radius=2.0):
+    """utils/clustering_utils.py:7-60 with every branch (the non-default graph / affinity types of
+    SURVEY 8(f-4)), the same sklearn / scipy / numpy calls as the reference."""
+    from sklearn import neighbors
+    import scipy.sparse
+    if neighbor_type == "knn":
+        graph = neighbors.kneighbors_graph(ptc[:, :3], n_neighbors=n_neighbors)
+    elif neighbor_type == "sym_knn":
+        graph = neighbors.kneighbors_graph(ptc[:, :3], n_neighbors=n_neighbors)
+        graph = graph + graph.T
+        graph.eliminate_zeros()
+    elif neighbor_type == "mutual_knn":
+        graph = neighbors.kneighbors_graph(ptc[:, :3], n_neighbors=n_neighbors)
+        graph = graph.multiply(graph.T)
+        graph.eliminate_zeros()
+    elif neighbor_type == "radius":
+        graph = neighbors.radius_neighbors_graph(ptc[:, :3], radius=radius)
+    elif neighbor_type == "radius_mutual_knn":
+        graph = neighbors.kneighbors_graph(ptc[:, :3], n_neighbors=n_neighbors)
+        graph = graph.multiply(graph.T)
+        graph = graph.multiply(neighbors.radius_neighbors_graph(ptc[:, :3], radius=radius))
+        graph.eliminate_zeros()
+    else:
+        raise NotImplementedError(neighbor_type)
+    graph = scipy.sparse.csr_matrix(graph)
+    data = graph.data.copy()
+    for r in range(graph.indptr.shape[0] - 1):
+        sl = slice(graph.indptr[r], graph.indptr[r + 1])
+        if affinity_type == "l1":
+            data[sl] = np.abs(pp[r] - pp[graph.indices[sl]])
+        elif affinity_type == "exp":
+            data[sl] = np.exp((pp[r] - pp[graph.indices[sl]]) ** 2)
+        elif affinity_type == "3d_l2_distance":
+            data[sl] = np.linalg.norm(ptc[r].reshape(1, -1) - ptc[graph.indices[sl]], axis=1)
+        else:
+            raise NotImplementedError(affinity_type)
+    return scipy.sparse.csr_matrix((data, graph.indices, graph.indptr), shape=graph.shape)
+
+
 def affinity_edges_bruteforce(ptc, pp, n_neighbors=70, radius=2.0):
     """Same edge set from first principles (small inputs): f64 squared distances
     (dx*dx + dy*dy) + dz*dz, j in kNN_k(i) with self excluded, mutual, d2 <= radius^2.
@@ -498,6 +537,78 @@ def closeness_fit(xz, d0=1e-2):
     area = (hi[0] - lo[0]) * (hi[1] - lo[1])
     corners = np.array([[hi[0], lo[1]], [lo[0], lo[1]], [lo[0], hi[1]], [hi[0], hi[1]]]) @ _axes(theta)
     return corners, theta, area
+
+
+def min_area_fit(points):
+    """utils/pointcloud_utils.py:88-146 (minimum_bounding_rectangle), literally: scipy ConvexHull,
+    the h-1 edges between consecutive vertices of its list, np.unique of |angle mod pi/2|."""
+    from scipy.spatial import ConvexHull
+    pi2 = np.pi / 2.
+    hull_points = points[ConvexHull(points).vertices]
+    edges = hull_points[1:] - hull_points[:-1]
+    angles = np.unique(np.abs(np.mod(np.arctan2(edges[:, 1], edges[:, 0]), pi2)))
+    rotations = np.vstack([np.cos(angles), np.cos(angles - pi2), np.cos(angles + pi2), np.cos(angles)]).T.reshape((-1, 2, 2))
+    rot_points = np.dot(rotations, hull_points.T)
+    min_x, max_x = np.nanmin(rot_points[:, 0], axis=1), np.nanmax(rot_points[:, 0], axis=1)
+    min_y, max_y = np.nanmin(rot_points[:, 1], axis=1), np.nanmax(rot_points[:, 1], axis=1)
+    areas = (max_x - min_x) * (max_y - min_y)
+    k = np.argmin(areas)
+    x1, x2, y1, y2, r = max_x[k], min_x[k], max_y[k], min_y[k], rotations[k]
+    rval = np.array([np.dot([x1, y2], r), np.dot([x2, y2], r), np.dot([x2, y1], r), np.dot([x1, y1], r)])
+    return rval, angles[k], areas[k]
+
+
+def pca_fit(cluster_ptc):
+    """utils/pointcloud_utils.py:148-165 (PCA_rectangle) with sklearn's PCA."""
+    import sklearn.decomposition
+    comp = sklearn.decomposition.PCA(n_components=2).fit(cluster_ptc).components_
+    on = cluster_ptc @ comp.T
+    min_x, max_x, min_y, max_y = on[:, 0].min(), on[:, 0].max(), on[:, 1].min(), on[:, 1].max()
+    rval = np.array([[max_x, min_y], [min_x, min_y], [min_x, max_y], [max_x, max_y]]) @ comp
+    return rval, np.arctan2(comp[0, 1], comp[0, 0]), (max_x - min_x) * (max_y - min_y)
+
+
+def variance_fit(cluster_ptc, delta=0.1):
+    """utils/pointcloud_utils.py:219-275 (variance_rectangle)."""
+    max_var, choose = -float("inf"), None
+
+    def comps(a):
+        return np.array([[np.cos(a), np.sin(a)], [-np.sin(a), np.cos(a)]])
+    for angle in np.arange(0, 90 + delta, delta):
+        angle = angle / 180. * np.pi
+        pr = cluster_ptc @ comps(angle).T
+        min_x, max_x, min_y, max_y = pr[:, 0].min(), pr[:, 0].max(), pr[:, 1].min(), pr[:, 1].max()
+        dx = np.vstack((pr[:, 0] - min_x, max_x - pr[:, 0])).min(axis=0)
+        dy = np.vstack((pr[:, 1] - min_y, max_y - pr[:, 1])).min(axis=0)
+        var = 0
+        if (dx < dy).sum() > 0:
+            var += -np.var(dx[dx < dy])
+        if (dy < dx).sum() > 0:
+            var += -np.var(dy[dy < dx])
+        if var > max_var:
+            max_var, choose = var, angle
+    angle = choose
+    pr = cluster_ptc @ comps(angle).T
+    min_x, max_x, min_y, max_y = pr[:, 0].min(), pr[:, 0].max(), pr[:, 1].min(), pr[:, 1].max()
+    if (max_x - min_x) < (max_y - min_y):
+        angle = choose + np.pi / 2
+        pr = cluster_ptc @ comps(angle).T
+        min_x, max_x, min_y, max_y = pr[:, 0].min(), pr[:, 0].max(), pr[:, 1].min(), pr[:, 1].max()
+    rval = np.array([[max_x, min_y], [min_x, min_y], [min_x, max_y], [max_x, max_y]]) @ comps(angle)
+    return rval, angle, (max_x - min_x) * (max_y - min_y)
+
+
+def fit_box_variant(cluster_rect, all_rect, fit_method):
+    """utils/pointcloud_utils.py:292-317 (get_obj) for the three non-default fit methods."""
+    xz = cluster_rect[:, [0, 2]]
+    corners, ry, area = {"min_zx_area_fit": min_area_fit, "PCA": pca_fit, "variance_to_edge": variance_fit}[fit_method](xz)
+    ry = ry * -1
+    l = np.linalg.norm(corners[0] - corners[1])
+    w = np.linalg.norm(corners[0] - corners[-1])
+    c = (corners[0] + corners[2]) / 2
+    bottom = lowest_point_in_footprint(all_rect, c, l, w, ry)
+    h = bottom - cluster_rect[:, 1].min()
+    return types.SimpleNamespace(t=np.array([c[0], bottom, c[1]]), l=l, w=w, h=h, ry=ry, volume=area * h)
 
 
 def lowest_point_in_footprint(all_rect, centre_xz, length, width, ry):

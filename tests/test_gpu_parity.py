@@ -625,6 +625,68 @@ def test_engine_reports_overflowed_capacity(golden_case):
         list(eng.SeedLabelEngine(seed=5, max_clusters=4).process([hb]))
 
 
+@pytest.mark.parametrize("neighbor_type,affinity_type", [("knn", "l1"), ("sym_knn", "exp"), ("mutual_knn", "3d_l2_distance"),
+                                                         ("radius", "l1"), ("radius_mutual_knn", "exp"),
+                                                         ("radius_mutual_knn", "3d_l2_distance")])
+def test_non_default_graph_and_affinity_types(golden_case, neighbor_type, affinity_type):
+    """every graph / affinity branch of precompute_affinity_matrix against the
+    reference's own sklearn / numpy calls: same edge set, l1 and 3d_l2 weights bit-equal (float32
+    arithmetic in numpy's order), exp within 2 float32 ulps of numpy's expf."""
+    from modest_b200.generate_cluster_mask.utils import clustering_utils as cu
+    from oracle import modest_oracle as orc
+    case, shape, g = golden_case("small")
+    mask = np.unpackbits(g["final_mask"])[:case.query.shape[0]].astype(bool)
+    ptc, pp = case.query[mask][:2500], g["pp"][mask][:2500]
+    k, radius = 12, 1.5
+    got = cu.precompute_affinity_matrix(ptc, pp, neighbor_type, affinity_type, k, radius)
+    ref = orc.affinity_graph_variant(ptc, pp, neighbor_type, affinity_type, k, radius)
+    ref.sort_indices()
+    got.sort_indices()
+    assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+    if affinity_type == "exp":
+        assert np.abs(got.data - ref.data).max() <= 3e-7 * np.abs(ref.data).max()
+    else:
+        assert np.array_equal(got.data, ref.data)
+    assert got.nnz > 0
+
+
+@pytest.mark.parametrize("fit_method", ["variance_to_edge", "PCA", "min_zx_area_fit"])
+def test_non_default_box_fitters(golden_case, fit_method):
+    """get_obj with the three other fit methods against the reference's own numpy /
+    sklearn / scipy code on the final clusters of a golden scan.  variance_to_edge reproduces numpy's
+    arithmetic (boxes to 1e-9); PCA equals sklearn's to rounding; min_zx_area_fit tries every hull
+    edge while the reference skips the one that closes scipy's vertex list, so it may find a smaller
+    rectangle there and must agree everywhere else."""
+    from modest_b200.generate_cluster_mask.utils import pointcloud_utils as pu
+    from oracle import modest_oracle as orc
+    case, shape, g = golden_case("small")
+    cal = orc.Calib(table=case.calib)
+    rect = cal.velo_to_rect(case.query[:, :3])
+    labels = g["labels_final"]
+    same = 0
+    ids = list(range(1, min(int(labels.max()), 12) + 1))
+    for cid in ids:
+        cl = rect[labels == cid]
+        ref = orc.fit_box_variant(cl, rect, fit_method)
+        got = pu.get_obj(cl, rect, fit_method)
+        tol = 1e-9 if fit_method == "variance_to_edge" else 1e-7
+        # footprint geometry (centre, sizes, heading) and, separately, the height: whether a cluster's own extreme
+        # points count as "strictly inside" the footprint hangs on the last bits of the rectangle, which only
+        # variance_to_edge reproduces
+        a = np.array([ref.t[0], ref.t[2], ref.l, ref.w])
+        b_ = np.array([got.t[0], got.t[2], got.l, got.w])
+        geo = np.abs(a - b_).max() <= tol * max(1.0, np.abs(a).max()) and abs(np.sin(ref.ry - got.ry)) <= 1e-7
+        height = abs(ref.h - got.h) <= tol * max(1.0, abs(ref.h)) and abs(ref.t[1] - got.t[1]) <= tol * max(1.0, abs(ref.t[1]))
+        if fit_method == "min_zx_area_fit" and not geo:
+            assert got.l * got.w <= ref.l * ref.w * (1 + 1e-9)      # the edge the reference skipped was the best one
+            continue
+        assert geo, (cid, a, b_, ref.ry, got.ry)
+        if fit_method == "variance_to_edge":
+            assert height and abs(ref.volume - got.volume) <= 1e-9 * max(1.0, ref.volume)
+        same += int(height)
+    assert same >= (len(ids) * 3) // 4
+
+
 def test_graph_dense_neighbourhoods_take_the_general_knn_kernel():
     """Neighbourhoods beyond the fast kNN kernel's scratch (a window row of > 4095 points, more
     than 1024 candidates inside the radius) are queued for the general kernel and its all-f64
