@@ -167,7 +167,9 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "scans_per_step": workers},
+            "config": {"workload": WORKLOAD, "scans_per_step_per_gpu": args.scans_per_step, "n_points": N_POINTS,
+                       "n_traversals": N_TRAV, "sample_scans_per_step": workers,
+                       "sample": "each step times a bounded sample of the workload: one scan per worker process"},
             "cpu_baseline": {"value": value, "unit": "scans/s", "cores": workers, "kind": "port",
                              "sample": f"{workers} scans per step, one per process (transform_points + cKDTree + sklearn, 1 thread each)",
                              "host": host_info()},

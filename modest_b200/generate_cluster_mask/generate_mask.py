@@ -74,7 +74,7 @@ def main(args: DictConfig):
         pps = [np.load(osp.join(args.data_paths.pp_score_path, f"{i:06d}.npy")) for i in chunk]
         calibs = [kitti_util.Calibration(osp.join(args.calib_path, f"{i:06d}.txt")) for i in chunk]
         batch = pl.make_batch(ptcs, pps, calibs, scan_ids=chunk)
-        res = pipe.run(batch, rng=rng_mode, seed=int(args.get("seed", 0)) + s0)
+        res = pipe.run(batch, rng=rng_mode, seed=int(args.get("seed", 0)))     # device draws are keyed by scan id: batch-invariant
         pipe.check_flags(res)
         labels = res.labels.cpu().numpy().astype(np.int64)
         boxes, n_boxes = res.boxes.cpu().numpy(), res.n_boxes.cpu().numpy()

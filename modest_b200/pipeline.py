@@ -353,6 +353,11 @@ class SeedLabelPipeline:
         rng="numpy":  parity mode (one scan per batch): both RANSAC fits draw from numpy's
                       global RandomState in the reference's order (first estimate_plane, then
                       filter_labels' own)."""
+        if stream is not None and stream != torch.cuda.current_stream():
+            # temporaries are allocated (and later freed) by torch's caching allocator on the CURRENT
+            # stream: make `stream` current for the whole call so kernels and allocations agree
+            with torch.cuda.stream(stream):
+                return self.run(b, rng=rng, seed=seed, want_debug=want_debug, stream=stream)
         cfg = self.cfg
         pe = cfg["plane_estimate"]
         r = BatchResult()
