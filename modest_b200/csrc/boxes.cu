@@ -659,52 +659,78 @@ __global__ void __launch_bounds__(256) box_bottom_kernel(
 
 struct VolumeCfg { double min_volume, max_volume; };
 
-// finish boxes (h, t.y, volume, keep), renumber surviving clusters, emit compact box rows
-__global__ void box_finalize_kernel(const int64_t* __restrict__ off, int max_clusters, const int32_t* __restrict__ n_clusters,
-                                    const ClusterStat* __restrict__ stats, BoxRec* __restrict__ boxes,
-                                    const unsigned long long* __restrict__ bottom, VolumeCfg cfg, const int32_t* __restrict__ new_id,
-                                    const int32_t* __restrict__ has_noise, int32_t* __restrict__ final_id /* (S,max_clusters+1) by filtered id */,
-                                    double* __restrict__ out_boxes /* (S,max_boxes,8) */, int max_boxes, int32_t* __restrict__ n_boxes,
-                                    int32_t* __restrict__ flags, int n_scans) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// finish boxes (h, t.y, volume, keep), renumber surviving clusters, emit compact box rows.
+// One CTA per scan: the keep decisions are independent per cluster, the box order (cluster id
+// order) comes from a block-wide ordered scan of the keep flags.
+__global__ void __launch_bounds__(256) box_finalize_kernel(
+    const int64_t* __restrict__ off, int max_clusters, const int32_t* __restrict__ n_clusters,
+    const ClusterStat* __restrict__ stats, BoxRec* __restrict__ boxes, const unsigned long long* __restrict__ bottom, VolumeCfg cfg,
+    const int32_t* __restrict__ new_id, const int32_t* __restrict__ has_noise, int32_t* __restrict__ final_id /* (S,max_clusters+1) by filtered id */,
+    double* __restrict__ out_boxes /* (S,max_boxes,8) */, int max_boxes, int32_t* __restrict__ n_boxes, int32_t* __restrict__ flags, int n_scans) {
+  const int s = blockIdx.x;
   if (s >= n_scans) return;
   const int C = min(n_clusters[s], max_clusters);
   int32_t* fid = final_id + (size_t)s * (max_clusters + 1);
   const int n = (int)(off[s + 1] - off[s]);
-  long long covered = 0;
-  int k = 0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __shared__ long long sh_cov[8];
+  __shared__ int sh_cnt[8];
+  __shared__ int sh_base;
   // pass 1: decide keep
-  for (int c = 0; c < C; ++c) {
-    if (!stats[(size_t)s * max_clusters + c].valid) continue;
+  long long covered = 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const ClusterStat st = stats[(size_t)s * max_clusters + c];
+    if (!st.valid) continue;
     BoxRec& b = boxes[(size_t)s * max_clusters + c];
-    if (stats[(size_t)s * max_clusters + c].valid == 2) { b.keep = 0; continue; }   // volume certified > max_volume
-    if (new_id[(size_t)s * max_clusters + c] <= 0) { b.keep = 0; continue; }   // id 0 is background for generate_mask.py:93
+    if (st.valid == 2) { b.keep = 0; continue; }                                 // volume certified > max_volume
+    if (new_id[(size_t)s * max_clusters + c] <= 0) { b.keep = 0; continue; }     // id 0 is background for generate_mask.py:93
     const unsigned long long bo = bottom[(size_t)s * max_clusters + c];
-    if (bo == 0ull) { b.keep = 0; atomicOr(flags, 8); continue; }      // empty footprint (reference would raise)
+    if (bo == 0ull) { b.keep = 0; atomicOr(flags, 8); continue; }                // empty footprint (reference would raise)
     const double bot = f64_from_ordered(bo);
     b.t[1] = bot;
     b.h = __dsub_rn(bot, b.ymin);
     b.volume = __dmul_rn(b.area, b.h);
     b.keep = (b.volume > cfg.min_volume && b.volume < cfg.max_volume) ? 1 : 0;
-    if (b.keep) covered += stats[(size_t)s * max_clusters + c].count;
+    if (b.keep) covered += st.count;
   }
+  covered = warp_sum(covered);
+  if (lane == 0) sh_cov[w] = covered;
+  if (threadIdx.x == 0) { fid[0] = 0; sh_base = 0; }
+  __syncthreads();                                                               // also publishes b.keep to the block
+  covered = 0;
+  for (int k = 0; k < 8; ++k) covered += sh_cov[k];
   // sorted(set(labels_filtered)) after rejected clusters were set to 0 (generate_mask.py:100-103)
   const int zero_present = (has_noise[s] || covered < n) ? 1 : 0;
-  fid[0] = 0;
-  for (int c = 0; c < C; ++c) {
-    if (!stats[(size_t)s * max_clusters + c].valid) continue;
-    const int filt = new_id[(size_t)s * max_clusters + c];          // 1..K (or 0..K-1 without noise)
-    const BoxRec& b = boxes[(size_t)s * max_clusters + c];
-    if (b.keep) {
-      if (k < max_boxes) {
-        double* o = out_boxes + ((size_t)s * max_boxes + k) * 8;
-        o[0] = b.t[0]; o[1] = b.t[1]; o[2] = b.t[2]; o[3] = b.l; o[4] = b.w; o[5] = b.h; o[6] = b.ry; o[7] = b.volume;
-      } else atomicOr(flags, 16);
-      if (filt >= 0 && filt <= max_clusters) fid[filt] = k + zero_present;
-      ++k;
-    } else if (filt >= 0 && filt <= max_clusters) fid[filt] = 0;
+  // pass 2: kept boxes in cluster order
+  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x;
+    bool valid = false, keep = false;
+    int filt = -1;
+    if (c < C && stats[(size_t)s * max_clusters + c].valid) {
+      valid = true;
+      filt = new_id[(size_t)s * max_clusters + c];                               // 1..K (or 0..K-1 without noise)
+      keep = boxes[(size_t)s * max_clusters + c].keep != 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) sh_cnt[w] = __popc(bal);
+    __syncthreads();
+    int k = sh_base + __popc(bal & ((1u << lane) - 1u));
+    for (int j = 0; j < w; ++j) k += sh_cnt[j];
+    if (valid) {
+      if (keep) {
+        if (k < max_boxes) {
+          const BoxRec& b = boxes[(size_t)s * max_clusters + c];
+          double* o = out_boxes + ((size_t)s * max_boxes + k) * 8;
+          o[0] = b.t[0]; o[1] = b.t[1]; o[2] = b.t[2]; o[3] = b.l; o[4] = b.w; o[5] = b.h; o[6] = b.ry; o[7] = b.volume;
+        } else atomicOr(flags, 16);
+        if (filt >= 0 && filt <= max_clusters) fid[filt] = k + zero_present;
+      } else if (filt >= 0 && filt <= max_clusters) fid[filt] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int j = 0; j < 8; ++j) t += sh_cnt[j]; sh_base += t; }
+    __syncthreads();
   }
-  n_boxes[s] = min(k, max_boxes);
+  if (threadIdx.x == 0) n_boxes[s] = min(sh_base, max_boxes);
 }
 
 __global__ void __launch_bounds__(256) apply_final_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ labels_filtered,
@@ -891,7 +917,7 @@ extern "C" int modest_filter_and_fit_batch(
   MODEST_LAUNCH_CHECK("box_fit_kernel");
   box_bottom_kernel<<<pgrid, 256, 0, stream>>>(d_off, rect, max_clusters, d_n_clusters, stats, boxes, bottom);
   MODEST_LAUNCH_CHECK("box_bottom_kernel");
-  box_finalize_kernel<<<(n_scans + 63) / 64, 64, 0, stream>>>(d_off, max_clusters, d_n_clusters, stats, boxes, bottom, vc, new_id, has_noise,
+  box_finalize_kernel<<<n_scans, 256, 0, stream>>>(d_off, max_clusters, d_n_clusters, stats, boxes, bottom, vc, new_id, has_noise,
                                                              final_id, d_boxes, max_boxes, d_n_boxes, d_flags, n_scans);
   MODEST_LAUNCH_CHECK("box_finalize_kernel");
   apply_final_kernel<<<pgrid, 256, 0, stream>>>(d_off, d_labels_filtered, max_clusters, final_id, d_labels_final);

@@ -413,9 +413,9 @@ def test_operator_dropins(golden_case):
     assert pu.objs2label(sel, cal) == str(g["label_text"])
     assert pu.objs2label(sel[:2], cal, with_score=True).count("-1.0000") == 2
     with pytest.raises(NotImplementedError):
-        pu.get_obj(rect[:20], rect, fit_method="PCA")
+        pu.get_obj(rect[:20], rect, fit_method="no_such_fit")
     with pytest.raises(NotImplementedError):
-        cu.precompute_affinity_matrix(ptc[:50], pp[:50], neighbor_type="knn")
+        cu.precompute_affinity_matrix(ptc[:50], pp[:50], neighbor_type="no_such_graph")
     xyz = ptc[:1000, :3]
     T = np.eye(4, dtype=np.float32); T[:3, 3] = (1.5, -2.25, 0.5); T[0, 1] = 0.01
     assert np.array_equal(pu.transform_points(xyz, T), orc.apply_pose(xyz, T))
