@@ -43,9 +43,10 @@ sys.path.insert(0, ROOT)
 
 N_POINTS, N_TRAV = 60000, 16
 # dram__bytes_read.sum + dram__bytes_write.sum of one pp_count_kernel launch over 24 scans, from the
-# `ncu --set full` capture summarised in profiles/r1b_pp_count_bench_launch_ncu_full_summary.csv
-# (425.8 MB read + 69.1 MB written); the kernel's traffic is proportional to the scans per launch
-PP_COUNT_DRAM_TRAFFIC_PER_SCAN = (425_806_080 + 69_080_320) / 24
+# round-2 `ncu --set full` capture of this bench's own launch, summarised in
+# profiles/r2_pp_count_bench_launch_ncu_full_summary.csv (425.9 MB read + 69.6 MB written; round 1:
+# 425.8 + 69.1); the kernel's traffic is proportional to the scans per launch
+PP_COUNT_DRAM_TRAFFIC_PER_SCAN = (425_871_360 + 69_556_224) / 24
 METRIC = "LiDAR scans/sec (PP-score+RANSAC+DBSCAN+NMS) @60k pts"
 WORKLOAD = "full seed-label pipeline, synthetic Lyft-shape drive (60k pts, 16 traversals x 1 frame of history per scan)"
 
@@ -365,7 +366,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "pp_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": int(PP_COUNT_DRAM_TRAFFIC_PER_SCAN * B),
-                     "traffic_source": "ncu --set full of a 24-scan launch (profiles/r1b_pp_count_bench_launch_ncu_full_summary.csv), "
+                     "traffic_source": "ncu --set full of a 24-scan launch (profiles/r2_pp_count_bench_launch_ncu_full_summary.csv), "
                                        "scaled to this launch's scan count",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(pp_alg_bytes), "kernel_ms": pp_ms,
