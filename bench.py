@@ -22,6 +22,8 @@ masks -> mutual-kNN graph -> DBSCAN -> second plane -> cluster gates -> box fit 
          copy bandwidth in MEASURED_PEAKS.json.
 `nusc`   BASELINE config 5 in small: nuScenes-shaped drive (34k points, 16 traversals x 16 frames
          of history per scan, max_hs=-1.3, centre removal), end to end incl. label files on disk.
+`lyft_f36` the Lyft shape at the real history depth (36 frames per traversal, 34.6 M history points
+         per scan), end to end.
 `--impl reference` times the reference's own CPU path (oracle port: SciPy cKDTree +
 scikit-learn, what the reference's programs call) on the host cores, on scans of the same drive.
 """
@@ -326,7 +328,14 @@ def run_ours(args):
     del engine
     torch.cuda.empty_cache()
 
-    nusc = None if args.no_nusc else run_nusc(args, rank, world, barrier)
+    nusc = lyft36 = None
+    if not args.no_nusc:
+        nusc = run_secondary(args, rank, world, barrier, "nusc", 16, 8,
+                             "nuScenes-shape drive: 34k-pt scans, 16 traversals x 16 history frames per scan, max_hs=-1.3, "
+                             "centre removal on history frames, label files written")
+        lyft36 = run_secondary(args, rank, world, barrier, "lyft", 36, 4,
+                               "Lyft-shape drive at the real history depth: 60k-pt scans, 16 traversals x 36 history frames "
+                               "per scan (34.6 M history points, 415 MB of PP input per scan)")
 
     if world > 1:
         t = torch.tensor([ms, e2e_s * 1e3, pp_ms, ms_single, pp_ms_overlapped], dtype=torch.float64, device="cuda")
@@ -377,6 +386,7 @@ def run_ours(args):
     }
     if nusc is not None:
         line["nusc"] = nusc
+        line["lyft_f36"] = lyft36
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
     if world == 1 and not args.no_cpu_baseline:
         n_cpu = 3
@@ -392,22 +402,24 @@ def run_ours(args):
     print(json.dumps(line))
 
 
-def run_nusc(args, rank, world, barrier):
-    """BASELINE config 5 in small: nuScenes-shaped drive end to end through the engine, label files written."""
+def run_secondary(args, rank, world, barrier, shape_name, F, Bn, what):
+    """A second drive end to end through the engine: nuScenes shape (BASELINE config 5 in small, label files
+    written) or Lyft shape with 36 history frames per traversal (the real Lyft history depth)."""
     import torch
     import torch.distributed as td
     from modest_b200 import dist
     from modest_b200 import engine as eng
     from modest_b200 import frames as fr
     from modest_b200 import synth
-    Bn, steps, F = 8, max(2, min(args.steps, 4)), 16
-    ds = drive("nusc", Bn * steps, rank, world, history_frames=F, id_base=2_000_000)
+    shape = synth.NUSC if shape_name == "nusc" else synth.LYFT
+    steps = max(2, min(args.steps, 4))
+    ds = drive(shape_name, Bn * steps, rank, world, history_frames=F, id_base=2_000_000 if shape.nusc else 3_000_000)
     ids = ds.scan_ids[:Bn * steps]
     source = fr.pinned_frame_source(ds.frames)
     for f in ds.frames:
         source(f)
-    cfg = dict(plane_estimate=dict(range=[[-70, 70], [-20, 20]], max_hs=synth.NUSC.max_hs, offset=0.05),
-               image_shape=list(synth.NUSC.image_shape))
+    cfg = dict(plane_estimate=dict(range=[[-70, 70], [-20, 20]], max_hs=shape.max_hs, offset=0.05),
+               image_shape=list(shape.image_shape))
     engine = eng.SeedLabelEngine(cfg, frame_source=source)
     warm_ids = ds.scan_ids[-Bn:]
     list(engine.process(fr.jobs_from_dataset(ds, warm_ids, Bn) * 5))     # ring touched; the warm-up scans' frames get cached
@@ -439,10 +451,13 @@ def run_nusc(args, rank, world, barrier):
         td.all_reduce(t, op=td.ReduceOp.MAX)
         e2e_s = float(t[0])
     hist_pts = sum(ds.frames[f].shape[0] for g in ds.history_frames(ids[0]) for f in g)
-    return {"workload": "nuScenes-shape drive: 34k-pt scans, 16 traversals x 16 history frames per scan, max_hs=-1.3, "
-                        "centre removal on history frames, label files written",
+    n_q = ds.frames[ids[0]].shape[0]
+    del engine
+    torch.cuda.empty_cache()
+    return {"workload": what,
             "e2e": {"value": len(ids) * world / e2e_s, "unit": "scans/s", "scans": len(ids) * world,
-                    "h2d_bytes_per_scan": int(h2d / len(ids)), "history_points_per_scan": int(hist_pts)},
+                    "h2d_bytes_per_scan": int(h2d / len(ids)), "history_points_per_scan": int(hist_pts),
+                    "pp_algorithmic_bytes_per_scan": int(12 * n_q + 12 * hist_pts + 4 * n_q)},
             "label_files": {"written": n_files, "seconds": round(write_s, 4)},
             "non_empty_labels": int(sum(1 for v in texts.values() if v))}
 
@@ -455,7 +470,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scans-per-step", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-nusc", action="store_true", help="skip the nuScenes-shape secondary measurement")
+    ap.add_argument("--no-nusc", action="store_true", help="skip the secondary measurements (nuScenes shape, Lyft F=36)")
     ap.add_argument("--streams", type=int, default=3, help="pipeline lanes of the device-resident loop")
     ap.add_argument("--e2e-depth", type=int, default=2, help="batches the engine keeps computing while the host reads back an older one")
     args = ap.parse_args()
