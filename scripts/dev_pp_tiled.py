@@ -13,8 +13,10 @@ from modest_b200 import _lib, pp_score, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 groups = [int(a) for a in sys.argv[2:]] or [0]
+F = int(os.environ.get("PP_F", 1))            # history frames per traversal
+NPTS = int(os.environ.get("PP_N", 60000))
 t0 = time.time()
-cases = [synth.make_scan_case(500 + i, synth.LYFT, n_traversals=16, n_points=60000) for i in range(n)]
+cases = [synth.make_scan_case(500 + i, synth.LYFT, n_traversals=16, frames_per_traversal=F, n_points=NPTS) for i in range(n)]
 print(f"{n} scans generated in {time.time() - t0:.1f}s", flush=True)
 b = pp_score.pack_batch([c.query_fixed for c in cases], [c.history for c in cases])
 lib = _lib.lib()

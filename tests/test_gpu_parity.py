@@ -63,7 +63,7 @@ def test_ransac_plane_parity_mode(golden_case, name):
     info = info.cpu().numpy()[0]
     assert float(dbg["thr"].cpu()[0]) == float(g["thr1"])                 # MAD threshold, f32 exact
     assert info[1] == int(g["n_trials1"])
-    assert abs(int(info[3]) - int(g["inlier_count1"])) <= 3               # borderline residuals may flip
+    assert int(info[3]) == int(g["inlier_count1"])                        # consensus-set size: exact on every golden
     assert np.abs(plane.cpu().numpy()[0] - g["plane"]).max() <= 1e-4
     # the stream must now sit where sklearn left it: the second fit reproduces plane2
     plane2, info2 = p.fit_planes(b, pl.FILTER_PLANE["max_hs"], pl.FILTER_PLANE["range"], rng="numpy")
@@ -838,3 +838,46 @@ def test_road_plane_files(golden_case, name, tmp_path):
 def ku_calib(g):
     from modest_b200.generate_cluster_mask.utils import kitti_util as ku
     return ku.Calibration(dict(P2=g["calib_P2"], Tr_velo_to_cam=g["calib_V2C"], R0_rect=g["calib_R0"]))
+
+
+def test_two_rank_programs_write_the_files_of_one_rank(tmp_path):
+    """SURVEY section 4, last row: the three programs under `torchrun --nproc-per-node 2` (each rank
+    takes its np.array_split shard, gen_label_files collates with the one all-gather) write the same
+    pp / seg / bbox / label files, byte for byte, as a single process.  Needs two GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    from modest_b200 import synth
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    data = str(tmp_path / "data")
+    meta = str(tmp_path / "meta")
+    synth.write_dataset(data, meta, synth.LYFT, n_traversals=3, frames_per_traversal=3, history_frames=1, n_points=20000)
+    progs = [("pre_compute_pp_score.py", []), ("generate_mask.py", ["rng=device", "batch_size=2"]), ("gen_label_files.py", [])]
+
+    def run(work, world):
+        os.makedirs(work, exist_ok=True)
+        for k, (prog, extra) in enumerate(progs):
+            ov = [f"data_root={data}", f"data_paths.track_path={meta}/track_list.pkl", f"data_paths.idx_info={meta}/valid_idx_info.pkl",
+                  f"data_paths.idx_list={meta}/train_idx.txt", f"data_paths.pp_score_path={work}/pp",
+                  f"data_paths.seg_save_dst={work}/seg", f"data_paths.bbox_info_save_dst={work}/bbox",
+                  f"data_paths.label_file_save_dst={work}/labels"] + extra
+            script = os.path.join(root, "modest_b200", "generate_cluster_mask", prog)
+            cmd = [sys.executable, script] + ov if world == 1 else \
+                [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                 "--master-port", str(29600 + k), script] + ov
+            subprocess.run(cmd, check=True, cwd=work, capture_output=True, timeout=600)
+
+    one, two = str(tmp_path / "w1"), str(tmp_path / "w2")
+    run(one, 1)
+    run(two, 2)
+    n = 0
+    for sub in ("pp", "seg", "bbox", "labels"):
+        names = sorted(f for f in os.listdir(os.path.join(one, sub)) if not f.endswith(".yaml"))
+        assert names == sorted(f for f in os.listdir(os.path.join(two, sub)) if not f.endswith(".yaml")) and names
+        for f in names:
+            with open(os.path.join(one, sub, f), "rb") as a, open(os.path.join(two, sub, f), "rb") as b:
+                assert a.read() == b.read(), (sub, f)
+            n += 1
+    assert n == 4 * 9
