@@ -167,6 +167,7 @@ __device__ __forceinline__ bool kth_by_histogram(Scan scan, int k_nn, T R2, int*
   ch.scale[0] = (T)kBins / (R2 * (T)(1.0 + 1e-6) + (T)1e-30);
   int need = k_nn;
   for (int round = 0; round < kMaxDepth; ++round) {
+    __syncwarp();                                   // the previous round's reads of hist[] are done
     for (int b = lane; b < kBins; b += 32) hist[b] = 0;
     __syncwarp();
     scan([&](bool live, T d2, int) {

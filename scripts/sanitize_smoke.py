@@ -21,4 +21,26 @@ ds = synth.make_track_dataset(synth.NUSC, n_traversals=3, frames_per_traversal=2
 e = eng.SeedLabelEngine(frame_source=fr.pinned_frame_source(ds.frames))
 out = list(e.process(fr.jobs_from_dataset(ds, ds.scan_ids, 4)))
 torch.cuda.synchronize()
-print("sanitize target ok:", sum(len(t) for _, ts in out for t in ts), "label bytes")
+# f-4 operator kernels (brute-force graphs, edge affinities, the three other fitters, lowest point)
+from modest_b200.generate_cluster_mask.utils import clustering_utils as cu, pointcloud_utils as pu  # noqa: E402
+rng = np.random.default_rng(0)
+pts = np.concatenate([rng.normal(0, 3, (700, 3)), rng.uniform(0, 1, (700, 1))], 1).astype(np.float32)
+ppv = rng.uniform(0, 1, 700).astype(np.float32)
+for nt, at in (("knn", "l1"), ("sym_knn", "exp"), ("mutual_knn", "3d_l2_distance"), ("radius", "l1"), ("radius_mutual_knn", "exp")):
+    g = cu.precompute_affinity_matrix(pts, ppv, nt, at, 9, 1.2)
+    assert g.nnz > 0
+rect = rng.normal(0, 4, (3000, 3))
+cl = rect[:400] * [0.5, 0.2, 0.2] + [3, 0, 2]
+rect = np.concatenate([rect, cl])
+for m in ("min_zx_area_fit", "PCA", "variance_to_edge", "closeness_to_edge"):
+    o = pu.get_obj(cl, rect, m)
+    assert np.isfinite([o.l, o.w, o.h, o.ry, o.volume]).all()
+# a scan with a huge cluster (box pre-rejection) and the parallel finalize
+big = synth.make_scan_case(9, synth.LYFT, n_traversals=2, n_points=30000)
+ppb = pp_score.count_neighbors_and_score(big.query_fixed, big.history)
+from modest_b200 import pipeline as pl  # noqa: E402
+pipe = pl.SeedLabelPipeline()
+r = pipe.run(pl.make_batch([big.query, case.query], [ppb, b[0]], [big.calib, case.calib], scan_ids=[9, 3]), rng="device", seed=2)
+pipe.check_flags(r)
+torch.cuda.synchronize()
+print("sanitize target ok:", sum(len(t) for _, ts in out for t in ts), "label bytes;", int(r.n_boxes.sum()), "boxes")
