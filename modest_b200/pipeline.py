@@ -153,12 +153,14 @@ class _Scratch:
 
     def __init__(self):
         self._bufs = {}
+        self.generation = 0       # (re)allocations so far: a captured CUDA graph is stale when this moves
 
     def get(self, name, numel, dtype, device):
         t = self._bufs.get(name)
         if t is None or t.numel() < numel or t.dtype != dtype or t.device != torch.device(device):
             t = torch.empty(max(int(numel), 1), dtype=dtype, device=device)
             self._bufs[name] = t
+            self.generation += 1
         return t
 
 

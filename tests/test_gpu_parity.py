@@ -576,6 +576,30 @@ def test_engine_frame_jobs_match_host_batches(shape_name):
     assert any(got.values())
 
 
+def test_engine_graph_replay_equals_eager_launches():
+    """The engine captures a lane's launch sequence into a CUDA graph the second time the lane sees
+    a batch of the same shape and replays it afterwards: label text byte-identical to the eager
+    path for every scan (replayed, captured and eager batches alike), a ragged batch in between
+    (different sizes: eager) does not disturb the captured graphs."""
+    from modest_b200 import engine as eng, frames as fr, synth
+    ds = synth.make_track_dataset(synth.LYFT, n_traversals=4, frames_per_traversal=12, n_points=6000, seed=123)
+    ids = ds.scan_ids
+    jobs = fr.jobs_from_dataset(ds, ids, 3)                       # 16 batches of 3 scans, one shape
+    odd = fr.jobs_from_dataset(ds, ids[:2], 2)                    # a batch of another shape
+    seq = jobs[:9] + odd + jobs[9:]
+    out = {}
+    for use in (False, True):
+        e = eng.SeedLabelEngine(seed=5, frame_source=fr.pinned_frame_source(ds.frames), use_graphs=use)
+        out[use] = [(tuple(b_ids), tuple(texts)) for b_ids, texts in e.process(iter(seq))]
+        if use:
+            n_slots = len(e.slots)
+            assert e.graph_replays >= len(jobs) - 2 * n_slots and e.launches_replayed > 0
+        else:
+            assert e.graph_replays == 0
+    assert out[True] == out[False]
+    assert any(t for _, texts in out[True] for t in texts)
+
+
 def test_nuscenes_shape_full_size_against_the_oracle():
     """BASELINE config 5's shape at full size: 34 000-point nuScenes-shaped scans of a drive, history
     of 3 traversals x 2 frames with the ego returns removed, plane_estimate.max_hs=-1.3, image
