@@ -388,11 +388,13 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_select_kernel(
           rk2 = bmin;                                      // every rank inside the block has this value
         } else {
           int rank = 0;
-          if (n_band > 1)
-            for (int l2 = 0; l2 < 32; ++l2) {
+          if (n_band > 1) {
+            const int nb = min(n_band, 32);                    // lanes beyond hold +inf and rank nobody down
+            for (int l2 = 0; l2 < nb; ++l2) {
               const double vv = __shfl_sync(0xffffffffu, mine, l2);
               rank += (vv < mine) || (vv == mine && l2 < lane);
             }
+          }
           const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < min(n_band, 32));
           if (hitl) rk2 = __shfl_sync(0xffffffffu, mine, __ffs(hitl) - 1);
           else if (lane == 0) atomicOr(flags, 1);
@@ -507,7 +509,8 @@ __device__ __forceinline__ float kth_in_list(const float* ld2, int cnt, int k_nn
       if (inbin > 32 && lane == 0) atomicOr(flags, 1);          // unresolved tie block
       if (have == 1) return __shfl_sync(0xffffffffu, mine, 0);
       int rank = 0;
-      for (int l2 = 0; l2 < 32; ++l2) {
+      const int nh = min(have, 32);                            // lanes beyond hold +inf and rank nobody down
+      for (int l2 = 0; l2 < nh; ++l2) {
         const float v = __shfl_sync(0xffffffffu, mine, l2);
         rank += (v < mine) || (v == mine && l2 < lane);
       }
@@ -568,31 +571,35 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
       const float eps = 4e-6f * (float)R2 + 1e-9f;             // f32 evaluation error bound, as in the general kernel
       const float band = 8.0f * eps;
       const float R2f_list = (float)R2 + band;
-      auto position = [&](unsigned short e) { return __shfl_sync(0xffffffffu, rkb, e >> kRowBits) + (int)(e & ((1u << kRowBits) - 1u)); };
+      // the rows' position ranges concatenated (rows hold ~19 points here: row-by-row trips would run
+      // half empty).  The non-empty rows are compacted into the low lanes -- lane k holds the first
+      // flat index and the first position of the k-th non-empty row -- so that a trip finds every
+      // lane's row with one OR-reduction of the rows' start lanes and two popcounts
+      int incl = rlen;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      const unsigned ne_rows = __ballot_sync(0xffffffffu, rlen > 0);
+      const int n_ne = __popc(ne_rows);
+      const int srow = lane < n_ne ? (int)__fns(ne_rows, 0, lane + 1) : 0;
+      int cexcl = __shfl_sync(0xffffffffu, incl - rlen, srow);
+      const int crkb = __shfl_sync(0xffffffffu, rkb, srow);
+      if (lane >= n_ne) cexcl = 0x7fffffff;
+      const unsigned lane_le = 0xffffffffu >> (31 - lane);
+      auto position = [&](unsigned short e) { return __shfl_sync(0xffffffffu, crkb, e >> kRowBits) + (int)(e & ((1u << kRowBits) - 1u)); };
       // ---- pass A: cache (d2, row|offset) of everything that could be within R2; count the sure ones ----
       int cnt = 0, sure = 0;
       {
-        // the rows' position ranges concatenated: every trip has 32 live lanes but the last
-        // (rows hold ~19 points here, so row-by-row trips run half empty)
-        int incl = rlen;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int u = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += u;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const int excl = incl - rlen;
-        int row = 0;                                            // of this lane's flat index; only ever advances
         for (int f0 = 0; f0 < total; f0 += 32) {
           const int idx = f0 + lane;
-          while (true) {
-            const int end = __shfl_sync(0xffffffffu, incl, row);
-            const bool adv = idx >= end && row < nrows - 1;
-            if (!__any_sync(0xffffffffu, adv)) break;
-            if (adv) ++row;
-          }
-          const int o = idx - __shfl_sync(0xffffffffu, excl, row);
-          const int kq = __shfl_sync(0xffffffffu, rkb, row) + o;
+          const int sl = cexcl - f0;                                // lane of this trip at which my row starts
+          const unsigned starts = __reduce_or_sync(0xffffffffu, (sl > 0 && sl < 32) ? 1u << sl : 0u);
+          const int row = __popc(__ballot_sync(0xffffffffu, cexcl <= f0)) - 1 + __popc(starts & lane_le);
+          const int o = idx - __shfl_sync(0xffffffffu, cexcl, row);
+          const int kq = __shfl_sync(0xffffffffu, crkb, row) + o;
           float d2 = 0.f;
           bool in = false;
           if (idx < total && kq != pos) {
@@ -667,11 +674,13 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
           rk2 = bmin;                                      // every rank inside the block has this value
         } else {
           int rank = 0;
-          if (n_band > 1)
-            for (int l2 = 0; l2 < 32; ++l2) {
+          if (n_band > 1) {
+            const int nb = min(n_band, 32);                    // lanes beyond hold +inf and rank nobody down
+            for (int l2 = 0; l2 < nb; ++l2) {
               const double vv = __shfl_sync(0xffffffffu, mine, l2);
               rank += (vv < mine) || (vv == mine && l2 < lane);
             }
+          }
           const unsigned hitl = __ballot_sync(0xffffffffu, rank == need - 1 && lane < min(n_band, 32));
           if (hitl) rk2 = __shfl_sync(0xffffffffu, mine, __ffs(hitl) - 1);
           else if (lane == 0) atomicOr(flags, 1);
