@@ -584,11 +584,18 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
       const int total = __shfl_sync(0xffffffffu, incl, 31);
       const unsigned ne_rows = __ballot_sync(0xffffffffu, rlen > 0);
       const int n_ne = __popc(ne_rows);
-      const int srow = lane < n_ne ? (int)__fns(ne_rows, 0, lane + 1) : 0;
-      int cexcl = __shfl_sync(0xffffffffu, incl - rlen, srow);
-      const int crkb = __shfl_sync(0xffffffffu, rkb, srow);
-      if (lane >= n_ne) cexcl = 0x7fffffff;
       const unsigned lane_le = 0xffffffffu >> (31 - lane);
+      // compaction through the (idle) histogram words: row r -> lane popc(non-empty rows below r)
+      int* scr = reinterpret_cast<int*>(hist32);
+      if (rlen > 0) {
+        const int k = __popc(ne_rows & (lane_le >> 1));
+        scr[k] = incl - rlen;
+        scr[32 + k] = rkb;
+      }
+      __syncwarp();
+      const int cexcl = lane < n_ne ? scr[lane] : 0x7fffffff;
+      const int crkb = lane < n_ne ? scr[32 + lane] : 0;
+      __syncwarp();
       auto position = [&](unsigned short e) { return __shfl_sync(0xffffffffu, crkb, e >> kRowBits) + (int)(e & ((1u << kRowBits) - 1u)); };
       // ---- pass A: cache (d2, row|offset) of everything that could be within R2; count the sure ones ----
       int cnt = 0, sure = 0;
