@@ -45,10 +45,11 @@ sys.path.insert(0, ROOT)
 
 N_POINTS, N_TRAV = 60000, 16
 # dram__bytes_read.sum + dram__bytes_write.sum of one pp_count_kernel launch over 24 scans, from the
-# round-2 `ncu --set full` capture of this bench's own launch, summarised in
-# profiles/r2_pp_count_bench_launch_ncu_full_summary.csv (425.9 MB read + 69.6 MB written; round 1:
-# 425.8 + 69.1); the kernel's traffic is proportional to the scans per launch
-PP_COUNT_DRAM_TRAFFIC_PER_SCAN = (425_871_360 + 69_556_224) / 24
+# latest `ncu --set full` capture of this bench's own launch (second session of round 2), summarised in
+# profiles/r2b_pp_count_knn_beta32_ncu_full_summary.csv (426.0 MB read + 69.6 MB written for 24 scans;
+# earlier captures: 425.9 + 69.6, round 1: 425.8 + 69.1); the kernel's traffic is proportional to
+# the scans per launch
+PP_COUNT_DRAM_TRAFFIC_PER_SCAN = (426_021_632 + 69_637_632) / 24
 METRIC = "LiDAR scans/sec (PP-score+RANSAC+DBSCAN+NMS) @60k pts"
 WORKLOAD = "full seed-label pipeline, synthetic Lyft-shape drive (60k pts, 16 traversals x 1 frame of history per scan)"
 
@@ -389,7 +390,7 @@ def run_ours(args):
                                 "afterwards; gpu_launches counts the kernels inside the replays"},
         "roofline": {"bound": "hbm", "kernel": "pp_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": int(PP_COUNT_DRAM_TRAFFIC_PER_SCAN * B),
-                     "traffic_source": "ncu --set full of a 24-scan launch (profiles/r2_pp_count_bench_launch_ncu_full_summary.csv), "
+                     "traffic_source": "ncu --set full of a 24-scan launch (profiles/r2b_pp_count_knn_beta32_ncu_full_summary.csv), "
                                        "scaled to this launch's scan count",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(pp_alg_bytes), "kernel_ms": pp_ms,

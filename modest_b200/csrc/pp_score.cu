@@ -426,25 +426,45 @@ __device__ __forceinline__ double numpy_strided_sum(int n, F term) {
   return r;
 }
 
+// One term of the entropy, -P ln(P + 1e-8) with P = count / (total + 1e-8): a function of the two
+// integers only.  The terms of all (total <= kEntS, count <= total) pairs are tabulated once per
+// call by the arithmetic below (4 656 logarithms instead of ~40 per query point; a scan's points
+// see ~28 neighbours in total on average, so nearly every row takes the table): same bits.
+constexpr int kEntS = 96;
+constexpr int kEntTabLen = (kEntS + 1) * (kEntS + 2) / 2;
+__device__ __forceinline__ double pp_entropy_term(int ct, double denom) {
+  if (ct == 0) return 0.0;                           // -0.0 * ln(1e-8) is exactly +0.0: skip the log
+  const double P = __ddiv_rn((double)ct, denom);
+  return __dmul_rn(-P, log(__dadd_rn(P, 1e-8)));
+}
+__global__ void pp_entropy_table_kernel(double* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kEntTabLen) return;
+  int tot = 0;
+  while ((tot + 1) * (tot + 2) / 2 <= i) ++tot;      // i = tot (tot + 1) / 2 + ct, ct <= tot
+  const int ct = i - tot * (tot + 1) / 2;
+  tab[i] = pp_entropy_term(ct, __dadd_rn((double)tot, 1e-8));
+}
+
 // H of one query point from its T neighbour counts (compute_ephe_score, :68-75)
 template <typename C>
-__device__ __forceinline__ float pp_entropy_of(int T, double logT, C count_of) {
+__device__ __forceinline__ float pp_entropy_of(int T, double logT, C count_of, const double* __restrict__ tab = nullptr) {
   long long tot = 0;
   for (int t = 0; t < T; ++t) tot += count_of(t);
+  if (tab != nullptr && tot <= kEntS) {
+    const double* row = tab + (int)tot * ((int)tot + 1) / 2;
+    const double acc = numpy_strided_sum(T, [&](int t) { return __ldg(row + count_of(t)); });
+    return (float)__ddiv_rn(acc, logT);
+  }
   const double denom = __dadd_rn((double)tot, 1e-8);
-  const double acc = numpy_strided_sum(T, [&](int t) {
-    const int ct = count_of(t);
-    if (ct == 0) return 0.0;                         // -0.0 * ln(1e-8) is exactly +0.0: skip the log
-    const double P = __ddiv_rn((double)ct, denom);
-    return __dmul_rn(-P, log(__dadd_rn(P, 1e-8)));
-  });
+  const double acc = numpy_strided_sum(T, [&](int t) { return pp_entropy_term(count_of(t), denom); });
   return (float)__ddiv_rn(acc, logT);
 }
 
 __global__ void __launch_bounds__(256) pp_entropy_kernel(
     const int* __restrict__ counts, const float4* __restrict__ sorted, const int64_t* __restrict__ q_off,
     const int64_t* __restrict__ count_off, const int32_t* __restrict__ trav_off, float* __restrict__ pp,
-    int32_t* __restrict__ counts_out /* (N,T) row-major per scan at count_off, or NULL */) {
+    int32_t* __restrict__ counts_out /* (N,T) row-major per scan at count_off, or NULL */, const double* __restrict__ tab) {
   const int s = blockIdx.y;
   const int T = trav_off[s + 1] - trav_off[s];
   const int64_t qbeg = q_off[s];
@@ -453,7 +473,7 @@ __global__ void __launch_bounds__(256) pp_entropy_kernel(
   const double logT = log((double)T);
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const int orig = __float_as_int(sorted[qbeg + k].w);
-    pp[qbeg + orig] = pp_entropy_of(T, logT, [&](int t) { return c[(size_t)t * n + k]; });
+    pp[qbeg + orig] = pp_entropy_of(T, logT, [&](int t) { return c[(size_t)t * n + k]; }, tab);
     if (counts_out)
       for (int t = 0; t < T; ++t) counts_out[count_off[s] + (size_t)orig * T + t] = c[(size_t)t * n + k];
   }
@@ -1129,6 +1149,7 @@ extern "C" size_t modest_pp_workspace_bytes(int n_scans, int64_t n_query_total, 
   add(sizeof(int) * (size_t)n_scans * col_tiles(grid_dim));                  // tile sums
   add(sizeof(float4) * (size_t)n_query_total);                               // sorted query
   add(sizeof(int32_t) * (size_t)kMaxTraversals);                             // traversal -> scan
+  add(sizeof(double) * (size_t)kEntTabLen);                                  // entropy terms of small (total, count) pairs
   // legacy path: counts [t][pos]; tiled path: the bins -- never both in one call
   const size_t legacy = sizeof(int) * (size_t)n_count_total, tiled = sizeof(float4) * (size_t)(bin_records > 0 ? bin_records : 0);
   add(legacy > tiled ? legacy : tiled);
@@ -1191,6 +1212,7 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
   int* tile_sums = ar.take<int>((size_t)n_scans * tiles);
   float4* sorted = ar.take<float4>(n_query_total);
   int32_t* trav_scan = ar.take<int32_t>(kMaxTraversals);
+  double* ent_tab = ar.take<double>(kEntTabLen);
   const size_t legacy_b = sizeof(int) * (size_t)n_count_total, tiled_b = sizeof(float4) * (size_t)(bin_records > 0 ? bin_records : 0);
   char* big = ar.take<char>(legacy_b > tiled_b ? legacy_b : tiled_b);
   int* counts = reinterpret_cast<int*>(big);
@@ -1264,9 +1286,11 @@ extern "C" int modest_pp_score_batch(const float* d_query_xyz, const int64_t* d_
     if (slot >= 0) { cudaEventRecord(g_prof_ev[2 * slot + 1], stream); ++g_prof_calls; }
     ++n_launched;
   }
-  pp_entropy_kernel<<<qgrid, 256, 0, stream>>>(counts, sorted, d_q_off, d_count_off, d_trav_off, d_pp, d_counts);
+  pp_entropy_table_kernel<<<(kEntTabLen + 255) / 256, 256, 0, stream>>>(ent_tab);
+  MODEST_LAUNCH_CHECK("pp_entropy_table_kernel");
+  pp_entropy_kernel<<<qgrid, 256, 0, stream>>>(counts, sorted, d_q_off, d_count_off, d_trav_off, d_pp, d_counts, ent_tab);
   MODEST_LAUNCH_CHECK("pp_entropy_kernel");
-  note_launch(n_launched + 1);
+  note_launch(n_launched + 2);
   return MODEST_OK;
 }
 
