@@ -19,7 +19,9 @@ b = pp_score.count_neighbors_and_score(case.query_fixed, case.history, return_co
 assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
 ds = synth.make_track_dataset(synth.NUSC, n_traversals=3, frames_per_traversal=2, history_frames=2, n_points=4000, seed=5)
 e = eng.SeedLabelEngine(frame_source=fr.pinned_frame_source(ds.frames))
-out = list(e.process(fr.jobs_from_dataset(ds, ds.scan_ids, 4)))
+jobs = fr.jobs_from_dataset(ds, ds.scan_ids, 4)
+out = list(e.process(jobs * 5))            # every lane sees a shape three times: eager, CUDA-graph capture, replay
+assert e.graph_replays > 0
 torch.cuda.synchronize()
 # f-4 operator kernels (brute-force graphs, edge affinities, the three other fitters, lowest point)
 from modest_b200.generate_cluster_mask.utils import clustering_utils as cu, pointcloud_utils as pu  # noqa: E402
