@@ -410,8 +410,14 @@ __global__ void __launch_bounds__(256) box_prereject_kernel(
   if (q1 && q2 && q3 && q4 && threadIdx.x == 0) st->valid = 2;
 }
 
-// grid (kAngleChunks, valid-cluster rank, scan); each warp scores a strided subset of the chunk
-__global__ void __launch_bounds__(256) box_beta32_kernel(
+// grid (kAngleChunks, valid-cluster rank, scan).  One THREAD per search angle, the cluster's points
+// broadcast from shared memory: every lane is busy whatever the cluster size and no heading needs a
+// warp reduction (one warp per angle with lanes over the points spent 28 % of its instructions on
+// the shuffles of the four extrema and the sum, and ran 30-60-point clusters with half the lanes).
+// The extrema are order-independent; the float32 sum is only used to shortlist angles (0.5 %).
+constexpr int kBetaThreads = 64;
+constexpr int kBetaStage = 512;
+__global__ void __launch_bounds__(kBetaThreads) box_beta32_kernel(
     const int64_t* __restrict__ off, int max_clusters, const ClusterStat* __restrict__ stats, const int32_t* __restrict__ cl_off,
     const int32_t* __restrict__ n_valid, const int32_t* __restrict__ valid_list, int max_valid, const float2* __restrict__ xz32,
     const double* __restrict__ trig, int n_angles, float d0, float* __restrict__ beta32) {
@@ -421,32 +427,42 @@ __global__ void __launch_bounds__(256) box_beta32_kernel(
   if (stats[(size_t)s * max_clusters + c].valid != 1) return;        // certified to fail the volume gate: not fitted
   const int n = stats[(size_t)s * max_clusters + c].count;
   const float2* __restrict__ pts = xz32 + off[s] + cl_off[(size_t)s * (max_clusters + 1) + c];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int per = (n_angles + gridDim.x - 1) / gridDim.x;
   const int a0 = blockIdx.x * per, a1 = min(n_angles, a0 + per);
   float* out = beta32 + ((size_t)s * max_valid + rank) * n_angles;
-  for (int a = a0 + w; a < a1; a += nw) {
+  __shared__ float2 sp[kBetaStage];
+  auto stage = [&](int c0, int m) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) sp[i] = __ldg(pts + c0 + i);
+    __syncthreads();
+  };
+  const bool resident = n <= kBetaStage;                              // staged once, read by both passes
+  if (resident) stage(0, n);
+  for (int ab = a0; ab < a1; ab += blockDim.x) {                      // block-uniform
+    const int a = min(ab + (int)threadIdx.x, a1 - 1);
     const float cs = (float)trig[a], sn = (float)trig[n_angles + a];
     float lox = 3e38f, hix = -3e38f, loy = 3e38f, hiy = -3e38f;
-    for (int i = lane; i < n; i += 32) {
-      const float2 p = __ldg(pts + i);
-      const float px = fmaf(p.y, sn, p.x * cs), py = fmaf(p.y, cs, -p.x * sn);
-      lox = fminf(lox, px); hix = fmaxf(hix, px); loy = fminf(loy, py); hiy = fmaxf(hiy, py);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
-      loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+    for (int c0 = 0; c0 < n; c0 += kBetaStage) {
+      const int m = min(kBetaStage, n - c0);
+      if (!resident) stage(c0, m);
+      for (int i = 0; i < m; ++i) {
+        const float2 p = sp[i];
+        const float px = fmaf(p.y, sn, p.x * cs), py = fmaf(p.y, cs, -p.x * sn);
+        lox = fminf(lox, px); hix = fmaxf(hix, px); loy = fminf(loy, py); hiy = fmaxf(hiy, py);
+      }
     }
     float beta = 0.f;
-    for (int i = lane; i < n; i += 32) {
-      const float2 p = __ldg(pts + i);
-      const float px = fmaf(p.y, sn, p.x * cs), py = fmaf(p.y, cs, -p.x * sn);
-      const float dx = fminf(px - lox, hix - px), dy = fminf(py - loy, hiy - py);
-      beta += __fdividef(1.0f, fmaxf(fminf(dx, dy), d0));
+    for (int c0 = 0; c0 < n; c0 += kBetaStage) {
+      const int m = min(kBetaStage, n - c0);
+      if (!resident) stage(c0, m);
+      for (int i = 0; i < m; ++i) {
+        const float2 p = sp[i];
+        const float px = fmaf(p.y, sn, p.x * cs), py = fmaf(p.y, cs, -p.x * sn);
+        const float dx = fminf(px - lox, hix - px), dy = fminf(py - loy, hiy - py);
+        beta += __fdividef(1.0f, fmaxf(fminf(dx, dy), d0));
+      }
     }
-    beta = warp_sum(beta);
-    if (lane == 0) out[a] = beta;
+    if (ab + (int)threadIdx.x < a1) out[ab + threadIdx.x] = beta;
   }
 }
 
@@ -908,7 +924,7 @@ extern "C" int modest_filter_and_fit_batch(
   box_center32_kernel<<<dim3(4, max_valid, n_scans), 256, 0, stream>>>(d_off, rect, max_clusters, stats, cl_off, members, d_n_valid,
                                                                       valid_list, max_valid, xz32);
   MODEST_LAUNCH_CHECK("box_center32_kernel");
-  box_beta32_kernel<<<dim3(kAngleChunks, max_valid, n_scans), 256, 0, stream>>>(d_off, max_clusters, stats, cl_off, d_n_valid, valid_list,
+  box_beta32_kernel<<<dim3(kAngleChunks, max_valid, n_scans), kBetaThreads, 0, stream>>>(d_off, max_clusters, stats, cl_off, d_n_valid, valid_list,
                                                                              max_valid, xz32, d_trig, n_angles, (float)d0, beta32);
   MODEST_LAUNCH_CHECK("box_beta32_kernel");
   box_fit_kernel<<<dim3(cblocks, n_scans), kFitThreads, 0, stream>>>(d_off, rect, max_clusters, d_n_clusters, stats, cl_off, members,
