@@ -37,15 +37,40 @@ __global__ void __launch_bounds__(256) cluster_stats_kernel(
   for (int k = 0; k < 4; ++k) pl[k] = planes[4 * s + k];
   const double nrm = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(pl[0], pl[0]), __dmul_rn(pl[1], pl[1])), __dmul_rn(pl[2], pl[2])));
   ClusterStat* st = stats + (size_t)s * max_clusters;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int c = labels[beg + i];
-    if (c < 0) continue;
-    if (c >= max_clusters) { atomicOr(flags, 4); continue; }
-    const float* p = ptc + (size_t)stride * (beg + i);
-    const unsigned long long d = f64_ordered(plane_distance2(p[0], p[1], p[2], pl, nrm));
-    atomicAdd(&st[c].count, 1);
-    atomicMin(&st[c].dmin, d);
-    atomicMax(&st[c].dmax, d);
+  const int lane = threadIdx.x & 31;
+  // consecutive returns of a beam mostly belong to one cluster: when every labelled lane of the warp
+  // holds the same cluster the warp reduces first and issues three atomics instead of 96 (the big
+  // clusters serialised thousands of atomics on one record)
+  for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += gridDim.x * blockDim.x) {   // warp-uniform
+    const int i = base + lane;
+    int c = i < n ? labels[beg + i] : -1;
+    if (c >= max_clusters) { atomicOr(flags, 4); c = -1; }
+    unsigned long long d = 0ull;
+    if (c >= 0) {
+      const float* p = ptc + (size_t)stride * (beg + i);
+      d = f64_ordered(plane_distance2(p[0], p[1], p[2], pl, nrm));
+    }
+    const unsigned vm = __ballot_sync(0xffffffffu, c >= 0);
+    if (vm == 0u) continue;
+    const int c0 = __shfl_sync(0xffffffffu, c, __ffs(vm) - 1);
+    if (__all_sync(0xffffffffu, c < 0 || c == c0)) {
+      unsigned long long lo = c >= 0 ? d : 0xffffffffffffffffull, hi = c >= 0 ? d : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+      }
+      if (lane == 0) {
+        atomicAdd(&st[c0].count, __popc(vm));
+        atomicMin(&st[c0].dmin, lo);
+        atomicMax(&st[c0].dmax, hi);
+      }
+    } else if (c >= 0) {
+      atomicAdd(&st[c].count, 1);
+      atomicMin(&st[c].dmin, d);
+      atomicMax(&st[c].dmax, d);
+    }
   }
 }
 
@@ -105,11 +130,23 @@ __global__ void __launch_bounds__(256) cluster_scatter_kernel(
   const int s = blockIdx.y;
   const int64_t beg = off[s];
   const int n = (int)(off[s + 1] - beg);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int c = labels[beg + i];
-    if (c < 0 || c >= max_clusters) continue;
-    const int pos = cl_off[(size_t)s * (max_clusters + 1) + c] + atomicAdd(&cl_fill[(size_t)s * max_clusters + c], 1);
-    members[beg + pos] = i;
+  const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += gridDim.x * blockDim.x) {   // warp-uniform
+    const int i = base + lane;
+    int c = i < n ? labels[beg + i] : -1;
+    if (c >= max_clusters) c = -1;
+    const unsigned vm = __ballot_sync(0xffffffffu, c >= 0);
+    if (vm == 0u) continue;
+    const int c0 = __shfl_sync(0xffffffffu, c, __ffs(vm) - 1);
+    if (__all_sync(0xffffffffu, c < 0 || c == c0)) {                 // one cluster in the warp: one atomic
+      int first = 0;
+      if (lane == 0) first = atomicAdd(&cl_fill[(size_t)s * max_clusters + c0], __popc(vm));
+      first = __shfl_sync(0xffffffffu, first, 0);
+      if (c >= 0) members[beg + cl_off[(size_t)s * (max_clusters + 1) + c0] + first + __popc(vm & ((1u << lane) - 1u))] = i;
+    } else if (c >= 0) {
+      const int pos = cl_off[(size_t)s * (max_clusters + 1) + c] + atomicAdd(&cl_fill[(size_t)s * max_clusters + c], 1);
+      members[beg + pos] = i;
+    }
   }
 }
 
