@@ -875,6 +875,8 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
   }
 }
 
+constexpr int kRowLanes = 8;            // lanes that share one graph row in the DBSCAN forest passes
+
 // Initial forest (ECL-CC style): every core point hangs under its smallest qualifying core
 // neighbour with a smaller index, then a few pointer-doubling sweeps shorten the chains, so the
 // union sweep below mostly finds "already together".
@@ -887,19 +889,26 @@ __global__ void __launch_bounds__(256) dbscan_init_kernel(
   const int64_t base = off[s];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int i = warp; i < n; i += nwarps) {
-    if (!core[base + i]) continue;
-    const int pre = eps_cnt ? eps_cnt[base + i] : -1;      // >= 0: only this prefix holds eps-edges
-    const int m = pre >= 0 ? pre : nbr_cnt[base + i];
+  // kRowLanes lanes per row, four rows per warp: the pass is a chain of dependent gathers (row ->
+  // neighbour -> its core flag), so what counts is how many rows a warp has in flight
+  const int gl = lane & (kRowLanes - 1), sub = lane / kRowLanes;
+  for (int iw = warp * (32 / kRowLanes); iw < n; iw += nwarps * (32 / kRowLanes)) {      // warp-uniform
+    const int i = iw + sub;
+    const bool active = i < n && core[base + i];
+    int pre = -1, m = 0;
+    if (active) {
+      pre = eps_cnt ? eps_cnt[base + i] : -1;      // >= 0: only this prefix holds eps-edges
+      m = pre >= 0 ? pre : nbr_cnt[base + i];
+    }
     const size_t row = (size_t)(base + i) * k_nn;
     int best = i;
-    for (int c = lane; c < m; c += 32) {
+    for (int c = gl; c < m; c += kRowLanes) {
       const int j = nbr[row + c];
       if (j < best && (pre >= 0 || (nbr_w && (double)nbr_w[row + c] <= eps)) && core[base + j]) best = j;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (lane == 0) parent[base + i] = best;
+    for (int o = kRowLanes / 2; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (gl == 0 && active) parent[base + i] = best;
   }
 }
 
@@ -927,8 +936,10 @@ __global__ void __launch_bounds__(256) dbscan_union_kernel(
   const int64_t base = off[s];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int i = warp; i < n; i += nwarps) {
-    if (!core[base + i]) continue;                 // warp-uniform
+  const int gl = lane & (kRowLanes - 1), sub = lane / kRowLanes;       // kRowLanes lanes per row, four rows per warp
+  for (int iw = warp * (32 / kRowLanes); iw < n; iw += nwarps * (32 / kRowLanes)) {
+    const int i = iw + sub;
+    if (i >= n || !core[base + i]) continue;
     const int pre = eps_cnt ? eps_cnt[base + i] : -1;
     const int m = pre >= 0 ? pre : nbr_cnt[base + i];
     const size_t row = (size_t)(base + i) * k_nn;
@@ -936,7 +947,7 @@ __global__ void __launch_bounds__(256) dbscan_union_kernel(
     // their root: two points with the same parent are already together (parents never leave
     // their tree), which spares the two dependent find() walks for almost every edge
     const int pi = parent[base + i];
-    for (int c = lane; c < m; c += 32) {
+    for (int c = gl; c < m; c += kRowLanes) {
       const int j = nbr[row + c];
       if (j < i && (pre >= 0 || (nbr_w && (double)nbr_w[row + c] <= eps)) && core[base + j] && parent[base + j] != pi)
         uf_union(parent + base, i, j);
