@@ -743,6 +743,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32, 8) knn_select_fast_kernel(
 // and never read the weights (order within a row carries no meaning; rows of more than 96 slots
 // are left unpartitioned and get nbr_eps_cnt = -1).
 constexpr int kMutualChunks = 3;        // 32-lane chunks held in registers for the partition
+constexpr int kMutualLanes = 4;         // lanes per row on the fused (eps-edges only) path: 385 (one warp) / 327 (8) / 312 (4) / 349 (2) us per 24 scans
 
 __global__ void __launch_bounds__(256) mutual_edges_kernel(
     const float4* __restrict__ kept, const int64_t* __restrict__ off, const int32_t* __restrict__ n_kept,
@@ -756,6 +757,50 @@ __global__ void __launch_bounds__(256) mutual_edges_kernel(
   const unsigned lt = (1u << lane) - 1u;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const bool partition = nbr_eps_cnt != nullptr && eps_first >= 0.0 && k_nn <= 32 * kMutualChunks;
+  if (partition && nbr_w == nullptr) {
+    // the fused path (eps-edges only): kMutualLanes lanes per row, several rows per warp -- the pass is
+    // a chain of dependent gathers (row -> neighbour's point, k-th distance, flags), so rows in flight
+    // count for more than full lanes (as in the DBSCAN forest passes)
+    const int gl = lane & (kMutualLanes - 1), sub = lane / kMutualLanes;
+    const unsigned gmask = ((kMutualLanes == 32 ? 0u : (1u << kMutualLanes)) - 1u) << (sub * kMutualLanes);
+    for (int iw = warp * (32 / kMutualLanes); iw < n; iw += nwarps * (32 / kMutualLanes)) {    // warp-uniform
+      const int i = iw + sub;
+      const bool act = i < n;
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      int m = 0;
+      if (act) { p = kept[base + i]; m = knn_cnt[base + i] & ~kTruncatedRow; }
+      const int32_t* row = knn + (size_t)(base + i) * k_nn;
+      int32_t* orow = nbr + (size_t)(base + i) * k_nn;
+      const int mmax = __reduce_max_sync(0xffffffffu, m);
+      int n_e = 0, n_o = 0;
+      for (int c0 = 0; c0 < mmax; c0 += kMutualLanes) {
+        const int c = c0 + gl;
+        bool in = false;
+        int j = 0;
+        float w = 0.f;
+        if (c < m) {
+          j = row[c];
+          const float4 q = kept[base + j];
+          const double d2 = sqdist_f64_seq(q.x, q.y, q.z, p.x, p.y, p.z);   // same expression as row j used
+          w = fabsf(__fsub_rn(p.w, q.w));
+          in = !(d2 > rk2[base + j]);
+          if (in && (knn_cnt[base + j] & kTruncatedRow)) {    // row j kept k of its tied neighbours: is i one of them?
+            const int32_t* rj = knn + (size_t)(base + j) * k_nn;
+            bool found = false;
+            for (int t = 0; t < k_nn; ++t) found |= rj[t] == i;
+            in = found;
+          }
+        }
+        const bool e = in && (double)w <= eps_first;
+        const unsigned be = __ballot_sync(0xffffffffu, e) & gmask, bo = __ballot_sync(0xffffffffu, in && !e) & gmask;
+        if (e) orow[n_e + __popc(be & lt)] = j;
+        n_e += __popc(be);
+        n_o += __popc(bo);
+      }
+      if (gl == 0 && act) { nbr_cnt[base + i] = n_e + n_o; nbr_eps_cnt[base + i] = n_e; }
+    }
+    return;
+  }
   for (int i = warp; i < n; i += nwarps) {
     const float4 p = kept[base + i];
     const int m = knn_cnt[base + i] & ~kTruncatedRow;
@@ -875,7 +920,11 @@ __device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
   }
 }
 
-constexpr int kRowLanes = 8;            // lanes that share one graph row in the DBSCAN forest passes
+// lanes that share one graph row in the DBSCAN forest passes.  Both passes are chains of dependent
+// gathers (row -> neighbour -> its core flag / parent), so what counts is how many rows a warp has in
+// flight, not how its lanes line up: measured per 24 scans with 32 / 16 / 8 / 4 / 2 / 1 lanes per row --
+// initial forest 179 / 167 / 126 / 105 / 105 / 79 us, union sweep 343 / 290 / 248 / 206 / 202 / 219 us
+constexpr int kInitLanes = 1, kUnionLanes = 2;
 
 // Initial forest (ECL-CC style): every core point hangs under its smallest qualifying core
 // neighbour with a smaller index, then a few pointer-doubling sweeps shorten the chains, so the
@@ -889,10 +938,8 @@ __global__ void __launch_bounds__(256) dbscan_init_kernel(
   const int64_t base = off[s];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  // kRowLanes lanes per row, four rows per warp: the pass is a chain of dependent gathers (row ->
-  // neighbour -> its core flag), so what counts is how many rows a warp has in flight
-  const int gl = lane & (kRowLanes - 1), sub = lane / kRowLanes;
-  for (int iw = warp * (32 / kRowLanes); iw < n; iw += nwarps * (32 / kRowLanes)) {      // warp-uniform
+  const int gl = lane & (kInitLanes - 1), sub = lane / kInitLanes;
+  for (int iw = warp * (32 / kInitLanes); iw < n; iw += nwarps * (32 / kInitLanes)) {      // warp-uniform
     const int i = iw + sub;
     const bool active = i < n && core[base + i];
     int pre = -1, m = 0;
@@ -902,12 +949,12 @@ __global__ void __launch_bounds__(256) dbscan_init_kernel(
     }
     const size_t row = (size_t)(base + i) * k_nn;
     int best = i;
-    for (int c = gl; c < m; c += kRowLanes) {
+    for (int c = gl; c < m; c += kInitLanes) {
       const int j = nbr[row + c];
       if (j < best && (pre >= 0 || (nbr_w && (double)nbr_w[row + c] <= eps)) && core[base + j]) best = j;
     }
 #pragma unroll
-    for (int o = kRowLanes / 2; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    for (int o = kInitLanes / 2; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
     if (gl == 0 && active) parent[base + i] = best;
   }
 }
@@ -936,8 +983,8 @@ __global__ void __launch_bounds__(256) dbscan_union_kernel(
   const int64_t base = off[s];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int gl = lane & (kRowLanes - 1), sub = lane / kRowLanes;       // kRowLanes lanes per row, four rows per warp
-  for (int iw = warp * (32 / kRowLanes); iw < n; iw += nwarps * (32 / kRowLanes)) {
+  const int gl = lane & (kUnionLanes - 1), sub = lane / kUnionLanes;
+  for (int iw = warp * (32 / kUnionLanes); iw < n; iw += nwarps * (32 / kUnionLanes)) {
     const int i = iw + sub;
     if (i >= n || !core[base + i]) continue;
     const int pre = eps_cnt ? eps_cnt[base + i] : -1;
@@ -947,7 +994,7 @@ __global__ void __launch_bounds__(256) dbscan_union_kernel(
     // their root: two points with the same parent are already together (parents never leave
     // their tree), which spares the two dependent find() walks for almost every edge
     const int pi = parent[base + i];
-    for (int c = gl; c < m; c += kRowLanes) {
+    for (int c = gl; c < m; c += kUnionLanes) {
       const int j = nbr[row + c];
       if (j < i && (pre >= 0 || (nbr_w && (double)nbr_w[row + c] <= eps)) && core[base + j] && parent[base + j] != pi)
         uf_union(parent + base, i, j);
