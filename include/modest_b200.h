@@ -45,6 +45,13 @@ const char* modest_last_error(void);
  * `gpu_launches`). */
 int64_t modest_launch_count(void);
 
+/* Stage A plumbing of the streaming engine (load_velo_scan, utils/pointcloud_utils.py:61, for every
+ * frame of pre_compute_pp_score.py:133-150): n host -> device copies enqueued on `stream` in one call.
+ * h_src[i] must be pinned host memory (the copies are asynchronous), d_dst[i] device memory of at
+ * least n_bytes[i] bytes.  The three arrays are host arrays. */
+int modest_upload_frames(const void* const* h_src, void* const* d_dst, const int64_t* n_bytes, int n,
+                         void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Stage B: bring scan frames into the fixed frame.
  * Replaces transform_points() (utils/pointcloud_utils.py:11-19: [p,1] @ Tr^T in float32) and,

@@ -27,6 +27,7 @@ SIGNATURES = {
     "modest_abi_version": (C.c_int, []),
     "modest_last_error": (C.c_char_p, []),
     "modest_launch_count": (_i64, []),
+    "modest_upload_frames": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     "modest_transform_frames_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _i64, C.c_int, _vp, _vp, _vp]),
     "modest_transform_gather_batch": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _i64, _vp, _vp, _vp]),
     "modest_pp_bin_records": (_i64, [_vp, _vp, C.c_int, _i64]),

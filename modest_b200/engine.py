@@ -215,8 +215,9 @@ class SeedLabelEngine:
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot.done)                # buffers free again?
             cache = self.frame_cache
-            q_t = [cache.get(int(f)) for f in jb.query_fid]
-            h_t = [cache.get(int(f)) for f in jb.hist_fid]
+            fids = [int(f) for f in jb.query_fid] + [int(f) for f in jb.hist_fid]
+            ts = cache.get_many(fids, stream=self.copy_stream)     # misses uploaded by one library call
+            q_t, h_t = ts[:len(jb.query_fid)], ts[len(jb.query_fid):]
             slot.frame_refs = q_t + h_t
             S, H = len(q_t), len(h_t)
             qn = np.array([t.shape[0] for t in q_t], dtype=np.int64)

@@ -18,6 +18,8 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
+from . import _lib
+
 # the 96-byte job record of modest_transform_gather_batch (include/modest_b200.h)
 FRAME_JOB = np.dtype([("src", "<u8"), ("dst_row", "<i8"), ("n", "<i4"), ("flags", "<i4"), ("T", "<f4", (16,)),
                       ("pad", "<i8")])
@@ -89,6 +91,36 @@ class DeviceFrameCache:
         self.h2d_bytes += n * 4
         self._d[fid] = t
         return t
+
+    def get_many(self, fids, stream=None):
+        """`get` for a list of frames with the uploads of all misses enqueued by one library call
+        (a batch of a drive can need ~800 frames the cache has not seen: one torch copy per frame
+        costs the host 30-80 us each, the library's loop 2-3 us)."""
+        out, todo = [], []
+        for fid in fids:
+            t = self._d.get(fid)
+            if t is not None:
+                self.hits += 1
+            else:
+                self.misses += 1
+                host = self.source(fid)
+                n = host.numel()
+                slab = self._room(n)
+                t = slab[0][slab[1]:slab[1] + n].view(host.shape)
+                slab[1] += (n + 3) // 4 * 4                     # frames stay 16-byte aligned
+                slab[2].append(fid)
+                self.h2d_bytes += n * 4
+                self._d[fid] = t
+                todo.append((host, t, 4 * n))
+            out.append(t)
+        if todo:
+            src = np.array([h.data_ptr() for h, _, _ in todo], dtype=np.uint64)
+            dst = np.array([t.data_ptr() for _, t, _ in todo], dtype=np.uint64)
+            nb = np.array([b for _, _, b in todo], dtype=np.int64)
+            _lib.check(_lib.lib().modest_upload_frames(src.ctypes.data, dst.ctypes.data, nb.ctypes.data, len(todo),
+                                                       _lib.stream_ptr(stream)), "modest_upload_frames")
+            self._keepalive = [h for h, _, _ in todo]           # host buffers stay referenced until the next call
+        return out
 
     def clear(self):
         self._d.clear()
