@@ -14,7 +14,6 @@ stages: the query scan in the fixed frame and the per-traversal history clouds
 """
 from __future__ import annotations
 
-import os
 import queue
 import threading
 import time
